@@ -1,0 +1,80 @@
+// Common definitions for the mickey_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MK_OK 0
+#define MK_ERR_INVALID -1
+#define MK_ERR_CUDA -2
+#define MK_ERR_MISSING_TENSOR -3
+#define MK_ERR_UNSUPPORTED -4
+
+namespace mk {
+
+// ---- GEMM ("D = A * B^T" with A [M,K] K-major fp16, B [N,K] K-major fp16, fp32 accumulate) ----------
+// One kernel family serves: ViT linears, patch embedding, 3x3 convolutions of the heads (as 9 row-shifted
+// K-slabs over a zero-padded NHWC image), the linear-attention projections, and the descriptor
+// correlation of the matcher.  The epilogue is selected at compile time.
+enum Epi : int {
+  EPI_STORE_H = 0,   // out_h = act(acc + bias)            fp16           (qkv, fc1+GELU, mlp.0+ReLU)
+  EPI_RESID_F = 1,   // out_f += gamma * (acc + bias)      fp32 in place  (attn.proj, mlp.fc2 + LayerScale + residual)
+  EPI_PATCH   = 2,   // out_f[row_map(m)] = acc + aux[m % tok][n]         (patch embed + bias + pos-embed)
+  EPI_CONV    = 3,   // out_h = mask(act(acc + bias + res_h) + aux)       (3x3 / 1x1 conv, BN folded, shortcut, PE)
+  EPI_STORE_F = 4,   // out_f = acc                        fp32           (linear-attention q,k,v)
+  EPI_LN      = 5,   // out = LN_128(acc) [+ out_f]        fp16 (+fp32)   (merge+norm1, mlp.2+norm2+residual)
+  EPI_LSE     = 6,   // row_sum[m] += sum_n exp(acc/T - shift)            (matcher pass 1)
+  EPI_DUAL    = 7,   // scores / kp_scores / final_scores                 (matcher pass 2)
+};
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+struct GemmParams {
+  int M, N;                 // logical output rows / cols per group
+  int k_chunks;             // number of 64-element K chunks in total (all taps)
+  int chunks_per_tap;       // K chunks per tap (= k_chunks when num_taps == 1)
+  int num_taps;
+  int tap_shift[9];         // A row shift per tap (3x3 conv over the flattened padded image)
+  int groups;               // blockIdx.z
+  int a_row_group_off, a_col_group_off, a_col_base;   // A coordinates added per group
+  int b_row_group_off;      // B rows added per group (usually N)
+  int act;
+  // epilogue operands (meaning depends on Epi)
+  const float* bias;  int bias_group_off;
+  const float* gamma; const float* beta; int ln_group_off;
+  float* out_f; long long out_f_ld; long long out_f_group_off;
+  __half* out_h; long long out_h_ld; long long out_h_group_off;
+  const __half* res_h; long long res_h_ld; long long res_h_group_off;
+  const float* aux; int aux_group_mask;   // pos table (EPI_PATCH: [tok, N]) / PE table (EPI_CONV: [rows_per_img, N])
+  int pad_h2, pad_w2;       // padded token grid (rows per image = pad_h2 * pad_w2); 0 = no pad masking
+  int tok_per_img;          // EPI_PATCH: patch tokens per image
+  float eps;
+  // matcher
+  int n_valid;              // valid rows == valid cols per pair
+  float inv_temp;
+  const float* shift;       // [groups] softmax shift per pair
+  const float* dustbin;     // device scalar or nullptr
+  float* row_sum;           // EPI_LSE out: [groups, n_valid]
+  const float* rs; const float* cs;     // EPI_DUAL in
+  const float* scr0; const float* scr1; // [groups, n_valid]
+  float* scores; float* kp_scores; float* final_scores;   // [groups, n_valid, n_valid]
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace mk
+
+#define MK_CUDA_CHECK(x)                                                                      \
+  do {                                                                                        \
+    cudaError_t e_ = (x);                                                                     \
+    if (e_ != cudaSuccess) {                                                                  \
+      mk::set_last_error("%s failed at %s:%d: %s", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return MK_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+namespace mk {
+void set_last_error(const char* fmt, ...);
+}

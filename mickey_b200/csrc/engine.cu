@@ -1,0 +1,527 @@
+// The C ABI (include/mickey_b200.h): handle, packed-weight registry, workspace carving and the kernel
+// sequence of the three stages (extract -> match -> solve).
+#include "../../include/mickey_b200.h"
+#include "gemm.h"
+#include "ops.h"
+
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace mk;
+
+struct Tensor { const void* ptr; int dtype; long long numel; };
+
+struct mk_handle {
+  int device;
+  mk_config cfg;
+  std::unordered_map<std::string, Tensor> tensors;
+  int geo_h = 0, geo_w = 0;
+  bool finalized = false;
+  long long launches = 0;
+};
+
+namespace {
+
+struct Geo {
+  int H, W, gh, gw, N, T, h2, w2, per_img, n_img;
+  long long M, Mp, R;
+};
+
+Geo make_geo(int n_pairs, int H, int W) {
+  Geo g;
+  g.H = H; g.W = W; g.gh = H / 14; g.gw = W / 14;
+  g.N = g.gh * g.gw; g.T = g.N + 1; g.h2 = g.gh + 2; g.w2 = g.gw + 2; g.per_img = g.h2 * g.w2;
+  g.n_img = 2 * n_pairs;
+  g.M = (long long)g.n_img * g.T; g.Mp = (long long)g.n_img * g.N; g.R = (long long)g.n_img * g.per_img;
+  return g;
+}
+
+constexpr int KPAD = 640;       // 3*14*14 = 588 padded to a multiple of 64
+constexpr int G = 4;            // heads: depth_head, det_offset, det_head, dsc_head
+
+// Bump allocator over the caller's workspace; with base == nullptr it only measures.
+struct Carver {
+  uint8_t* base; size_t off = 0;
+  explicit Carver(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  template <typename T> T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct Workspace {
+  // backbone
+  __half* P; float* X; __half* XN; __half* QKV; __half* ATT; __half* H1;
+  // heads
+  __half* F; __half *T1, *S1, *O1, *T2, *S2, *O2, *T3, *S3, *CAT, *MSG, *HM, *T4k, *S4k, *T4d;
+  float *X32, *QKV32, *KV, *Y4k, *Y4d;
+  // head outputs kept for the matcher
+  float* score_raw; __half* DSCX; float* nrm2; float* scr_copy;
+  // matcher
+  float *shift, *row_sum, *col_sum;
+  // solver
+  void* samp_ws; int* idx; float* xyw; float* hyp_scores; float* hyp_Rt; int* status; int* best_hyp;
+  size_t bytes;
+};
+
+Workspace carve(void* base, const mk_config& c, const Geo& g, int n_pairs) {
+  Workspace w;
+  Carver cv(base);
+  const size_t D = c.embed_dim, M = g.M, R = g.R;
+  const int* bd = c.block_dims;
+  w.P = cv.take<__half>((size_t)g.Mp * KPAD);
+  w.X = cv.take<float>(M * D);
+  w.XN = cv.take<__half>(M * D);
+  w.QKV = cv.take<__half>(M * 3 * D);
+  w.ATT = cv.take<__half>(M * D);
+  w.H1 = cv.take<__half>(M * 4 * D);
+  w.F = cv.take<__half>(R * D);
+  w.T1 = cv.take<__half>(R * G * bd[0]); w.S1 = cv.take<__half>(R * G * bd[0]); w.O1 = cv.take<__half>(R * G * bd[0]);
+  w.T2 = cv.take<__half>(R * G * bd[1]); w.S2 = cv.take<__half>(R * G * bd[1]); w.O2 = cv.take<__half>(R * G * bd[1]);
+  w.T3 = cv.take<__half>(R * G * bd[2]); w.S3 = cv.take<__half>(R * G * bd[2]);
+  w.CAT = cv.take<__half>(R * G * 256); w.MSG = cv.take<__half>(R * G * 128); w.HM = cv.take<__half>(R * G * 256);
+  w.T4k = cv.take<__half>(R * 3 * bd[3]); w.S4k = cv.take<__half>(R * 3 * bd[3]); w.T4d = cv.take<__half>(R * c.desc_dim);
+  w.X32 = cv.take<float>(R * G * 128); w.QKV32 = cv.take<float>(R * G * 384);
+  w.KV = cv.take<float>((size_t)g.n_img * G * 8 * 272);
+  w.Y4k = cv.take<float>(R * 3 * bd[3]); w.Y4d = cv.take<float>(R * c.desc_dim);
+  w.score_raw = cv.take<float>((size_t)g.n_img * g.N);
+  w.DSCX = cv.take<__half>((size_t)g.n_img * g.N * 384);
+  w.nrm2 = cv.take<float>((size_t)g.n_img * g.N);
+  w.scr_copy = cv.take<float>((size_t)g.n_img * g.N);
+  w.shift = cv.take<float>(n_pairs);
+  w.row_sum = cv.take<float>((size_t)n_pairs * g.N); w.col_sum = cv.take<float>((size_t)n_pairs * g.N);
+  const size_t streams = (size_t)n_pairs * c.it_matches;
+  w.samp_ws = cv.take<uint8_t>(sampler_workspace_bytes(n_pairs, c.it_matches));
+  w.idx = cv.take<int>(streams * c.num_sampled);
+  w.xyw = cv.take<float>(streams * 8 * c.num_sampled);
+  w.hyp_scores = cv.take<float>(streams * c.it_ransac);
+  w.hyp_Rt = cv.take<float>(streams * c.it_ransac * 12);
+  w.status = cv.take<int>(4);
+  w.best_hyp = cv.take<int>(n_pairs);
+  w.bytes = cv.off + 256;
+  return w;
+}
+
+// ---- weight lookup ---------------------------------------------------------------------------------------
+struct Lookup {
+  mk_handle* h; bool ok = true;
+  const void* get(const std::string& name, int dtype, long long numel) {
+    auto it = h->tensors.find(name);
+    if (it == h->tensors.end()) { set_last_error("missing tensor '%s'", name.c_str()); ok = false; return nullptr; }
+    if (it->second.dtype != dtype || it->second.numel != numel) {
+      set_last_error("tensor '%s': expected dtype %d numel %lld, got dtype %d numel %lld", name.c_str(), dtype, numel,
+                     it->second.dtype, it->second.numel);
+      ok = false; return nullptr;
+    }
+    return it->second.ptr;
+  }
+  const float* f(const std::string& n, long long numel) { return reinterpret_cast<const float*>(get(n, 0, numel)); }
+  const __half* hh(const std::string& n, long long numel) { return reinterpret_cast<const __half*>(get(n, 1, numel)); }
+};
+
+GemmParams base_params(long long M, int N, int K) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = N; p.k_chunks = K / 64; p.chunks_per_tap = p.k_chunks; p.num_taps = 1; p.groups = 1;
+  return p;
+}
+
+void set_conv_taps(GemmParams& p, int cin, int w2, bool three) {
+  p.chunks_per_tap = cin / 64;
+  if (three) {
+    p.num_taps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) p.tap_shift[ky * 3 + kx] = (ky - 1) * w2 + (kx - 1);
+  } else {
+    p.num_taps = 1; p.tap_shift[0] = 0;
+  }
+  p.k_chunks = p.num_taps * p.chunks_per_tap;
+}
+
+#define MK_TRY(x) do { int rc_ = (x); if (rc_ != MK_OK) return rc_; } while (0)
+
+int gemm(mk_handle* h, int epi, const void* a, long long a_rows, long long a_cols, const void* b, long long b_rows,
+         long long b_cols, const GemmParams& p, cudaStream_t st) {
+  GemmOperand A{a, a_rows, a_cols, a_cols}, B{b, b_rows, b_cols, b_cols};
+  h->launches++;
+  return launch_gemm(epi, A, B, p, st);
+}
+
+// ---- stage 1 ----------------------------------------------------------------------------------------------
+int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, float* kps, float* depth, float* scr,
+                float* dsc, Workspace& w, cudaStream_t st) {
+  const mk_config& c = h->cfg;
+  const Geo g = make_geo(n_pairs, H, W);
+  const int D = c.embed_dim;
+  Lookup L{h};
+  // -- tokens: patch embedding + cls + position embedding (dinov2.py:191-200)
+  MK_TRY(patch_gather(images, w.P, g.n_img, H, W, KPAD, w.X, L.f("patch.clspos", D), D, st)); h->launches++;
+  {
+    GemmParams p = base_params(g.Mp, D, KPAD);
+    p.aux = L.f("patch.posb", (long long)g.N * D); p.tok_per_img = g.N; p.out_f = w.X; p.out_f_ld = D;
+    const __half* wt = L.hh("patch.w", (long long)D * KPAD);
+    if (!L.ok) return MK_ERR_MISSING_TENSOR;
+    MK_TRY(gemm(h, EPI_PATCH, w.P, g.Mp, KPAD, wt, D, KPAD, p, st));
+  }
+  // -- transformer blocks (layers/block.py:105-106)
+  for (int i = 0; i < c.depth; ++i) {
+    const std::string b = "blk" + std::to_string(i) + ".";
+    const float *ln1w = L.f(b + "ln1.w", D), *ln1b = L.f(b + "ln1.b", D), *ln2w = L.f(b + "ln2.w", D), *ln2b = L.f(b + "ln2.b", D);
+    const __half *wqkv = L.hh(b + "qkv.w", 3LL * D * D), *wproj = L.hh(b + "proj.w", (long long)D * D);
+    const __half *wfc1 = L.hh(b + "fc1.w", 4LL * D * D), *wfc2 = L.hh(b + "fc2.w", 4LL * D * D);
+    const float *bqkv = L.f(b + "qkv.b", 3 * D), *bproj = L.f(b + "proj.b", D), *bfc1 = L.f(b + "fc1.b", 4 * D), *bfc2 = L.f(b + "fc2.b", D);
+    const float *ls1 = L.f(b + "ls1", D), *ls2 = L.f(b + "ls2", D);
+    if (!L.ok) return MK_ERR_MISSING_TENSOR;
+    MK_TRY(layernorm(w.X, ln1w, ln1b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st)); h->launches++;
+    { GemmParams p = base_params(g.M, 3 * D, D); p.bias = bqkv; p.out_h = w.QKV; p.out_h_ld = 3 * D;
+      MK_TRY(gemm(h, EPI_STORE_H, w.XN, g.M, D, wqkv, 3 * D, D, p, st)); }
+    MK_TRY(attention(w.QKV, w.ATT, g.n_img, g.T, D, c.heads, st)); h->launches++;
+    { GemmParams p = base_params(g.M, D, D); p.bias = bproj; p.gamma = ls1; p.out_f = w.X; p.out_f_ld = D;
+      MK_TRY(gemm(h, EPI_RESID_F, w.ATT, g.M, D, wproj, D, D, p, st)); }
+    MK_TRY(layernorm(w.X, ln2w, ln2b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st)); h->launches++;
+    { GemmParams p = base_params(g.M, 4 * D, D); p.bias = bfc1; p.act = ACT_GELU; p.out_h = w.H1; p.out_h_ld = 4 * D;
+      MK_TRY(gemm(h, EPI_STORE_H, w.XN, g.M, D, wfc1, 4 * D, D, p, st)); }
+    { GemmParams p = base_params(g.M, D, 4 * D); p.bias = bfc2; p.gamma = ls2; p.out_f = w.X; p.out_f_ld = D;
+      MK_TRY(gemm(h, EPI_RESID_F, w.H1, g.M, 4 * D, wfc2, D, 4 * D, p, st)); }
+  }
+  // -- final norm, drop cls, scatter into the zero-padded NHWC feature image (dinov2.py:230-233, mickey_extractor.py:49-51)
+  MK_CUDA_CHECK(cudaMemsetAsync(w.F, 0, (size_t)g.R * D * sizeof(__half), st));
+  MK_TRY(layernorm(w.X, L.f("norm.w", D), L.f("norm.b", D), w.F, (int)g.M, D, 1e-6f, 1, g.gh, g.gw, st)); h->launches++;
+  if (!L.ok) return MK_ERR_MISSING_TENSOR;
+
+  // -- heads: three grouped residual blocks (extractor_utils.py:28-35; G = 4 heads side by side in channels)
+  const int* bd = c.block_dims;
+  struct Rb { const char* name; const __half* in; int cin; int in_goff; __half *T, *S, *O; int cout; };
+  const Rb rbs[3] = {{"rb1", w.F, D, 0, w.T1, w.S1, w.O1, bd[0]},
+                     {"rb2", w.O1, bd[0], bd[0], w.T2, w.S2, w.O2, bd[1]},
+                     {"rb3", w.O2, bd[1], bd[1], w.T3, w.S3, nullptr, bd[2]}};
+  if (bd[2] != 128) { set_last_error("KP_HEADS.BLOCKS_DIM[2] must be 128 (transformer width)"); return MK_ERR_UNSUPPORTED; }
+  for (int r = 0; r < 3; ++r) {
+    const Rb& rb = rbs[r];
+    const std::string n = std::string(rb.name) + ".";
+    const long long in_cols = (r == 0) ? D : (long long)G * rb.cin;
+    const __half *wc1 = L.hh(n + "c1.w", (long long)G * rb.cout * 9 * rb.cin), *wsc = L.hh(n + "sc.w", (long long)G * rb.cout * rb.cin);
+    const __half* wc2 = L.hh(n + "c2.w", (long long)G * rb.cout * 9 * rb.cout);
+    const float *b1 = L.f(n + "c1.b", G * rb.cout), *b2 = L.f(n + "c2.b", G * rb.cout);
+    if (!L.ok) return MK_ERR_MISSING_TENSOR;
+    {  // conv1 + bn1 + relu
+      GemmParams p = base_params(g.R, rb.cout, 64); set_conv_taps(p, rb.cin, g.w2, true);
+      p.groups = G; p.a_col_group_off = rb.in_goff; p.b_row_group_off = rb.cout; p.bias = b1; p.bias_group_off = rb.cout;
+      p.act = ACT_RELU; p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_h = rb.T; p.out_h_ld = (long long)G * rb.cout; p.out_h_group_off = rb.cout;
+      MK_TRY(gemm(h, EPI_CONV, rb.in, g.R, in_cols, wc1, (long long)G * rb.cout, 9LL * rb.cin, p, st));
+    }
+    {  // 1x1 shortcut
+      GemmParams p = base_params(g.R, rb.cout, 64); set_conv_taps(p, rb.cin, g.w2, false);
+      p.groups = G; p.a_col_group_off = rb.in_goff; p.b_row_group_off = rb.cout;
+      p.out_h = rb.S; p.out_h_ld = (long long)G * rb.cout; p.out_h_group_off = rb.cout;
+      MK_TRY(gemm(h, EPI_CONV, rb.in, g.R, in_cols, wsc, (long long)G * rb.cout, rb.cin, p, st));
+    }
+    {  // conv2 + bn2 + shortcut + relu (+ sine position encoding and fp32 copy after block 3)
+      GemmParams p = base_params(g.R, rb.cout, 64); set_conv_taps(p, rb.cout, g.w2, true);
+      p.groups = G; p.a_col_group_off = rb.cout; p.b_row_group_off = rb.cout; p.bias = b2; p.bias_group_off = rb.cout;
+      p.res_h = rb.S; p.res_h_ld = (long long)G * rb.cout; p.res_h_group_off = rb.cout;
+      p.act = ACT_RELU; p.pad_h2 = g.h2; p.pad_w2 = g.w2;
+      if (r < 2) { p.out_h = rb.O; p.out_h_ld = (long long)G * rb.cout; p.out_h_group_off = rb.cout; }
+      else {
+        p.out_h = w.CAT; p.out_h_ld = G * 256; p.out_h_group_off = 256;
+        p.out_f = w.X32; p.out_f_ld = G * 128; p.out_f_group_off = 128;
+        p.aux = L.f("head.pe", (long long)g.per_img * 128);
+        p.aux_group_mask = (c.kp_pos_enc ? 0x7 : 0) | (c.dsc_pos_enc ? 0x8 : 0);
+        if (!L.ok) return MK_ERR_MISSING_TENSOR;
+      }
+      MK_TRY(gemm(h, EPI_CONV, rb.T, g.R, (long long)G * rb.cout, wc2, (long long)G * rb.cout, 9LL * rb.cout, p, st));
+    }
+  }
+  // -- linear-attention transformer, 3 layers (att_layers/transformer_utils.py:40-66)
+  for (int l = 0; l < 3; ++l) {
+    const std::string n = "att" + std::to_string(l) + ".";
+    const __half *wqkv = L.hh(n + "qkv.w", (long long)G * 384 * 128), *wmerge = L.hh(n + "merge.w", (long long)G * 128 * 128);
+    const __half *wm0 = L.hh(n + "mlp0.w", (long long)G * 256 * 256), *wm2 = L.hh(n + "mlp2.w", (long long)G * 128 * 256);
+    const float *n1w = L.f(n + "n1.w", G * 128), *n1b = L.f(n + "n1.b", G * 128), *n2w = L.f(n + "n2.w", G * 128), *n2b = L.f(n + "n2.b", G * 128);
+    if (!L.ok) return MK_ERR_MISSING_TENSOR;
+    { GemmParams p = base_params(g.R, 384, 128); p.groups = G; p.a_col_group_off = 256; p.b_row_group_off = 384;
+      p.out_f = w.QKV32; p.out_f_ld = G * 384; p.out_f_group_off = 384;
+      MK_TRY(gemm(h, EPI_STORE_F, w.CAT, g.R, G * 256, wqkv, G * 384, 128, p, st)); }
+    MK_TRY(linattn_kv(w.QKV32, w.KV, g.n_img, G, g.h2, g.w2, st)); h->launches++;
+    MK_TRY(linattn_msg(w.QKV32, w.KV, w.MSG, g.n_img, G, g.h2, g.w2, 1e-6f, st)); h->launches++;
+    { GemmParams p = base_params(g.R, 128, 128); p.groups = G; p.a_col_group_off = 128; p.b_row_group_off = 128;
+      p.gamma = n1w; p.beta = n1b; p.ln_group_off = 128; p.eps = 1e-5f;
+      p.out_h = w.CAT + 128; p.out_h_ld = G * 256; p.out_h_group_off = 256;
+      MK_TRY(gemm(h, EPI_LN, w.MSG, g.R, G * 128, wmerge, G * 128, 128, p, st)); }
+    { GemmParams p = base_params(g.R, 256, 256); p.groups = G; p.a_col_group_off = 256; p.b_row_group_off = 256; p.act = ACT_RELU;
+      p.out_h = w.HM; p.out_h_ld = G * 256; p.out_h_group_off = 256;
+      MK_TRY(gemm(h, EPI_STORE_H, w.CAT, g.R, G * 256, wm0, G * 256, 256, p, st)); }
+    { GemmParams p = base_params(g.R, 128, 256); p.groups = G; p.a_col_group_off = 256; p.b_row_group_off = 128;
+      p.gamma = n2w; p.beta = n2b; p.ln_group_off = 128; p.eps = 1e-5f;
+      p.out_f = w.X32; p.out_f_ld = G * 128; p.out_f_group_off = 128;
+      p.out_h = w.CAT; p.out_h_ld = G * 256; p.out_h_group_off = 256;
+      if (l == 2) { p.pad_h2 = g.h2; p.pad_w2 = g.w2; }       // zero the pad rows again before the next 3x3 conv
+      MK_TRY(gemm(h, EPI_LN, w.HM, g.R, G * 256, wm2, G * 128, 256, p, st)); }
+  }
+  // -- residual block 4: three keypoint heads (128 -> 64, with shortcut conv) and the descriptor head (128 -> desc_dim)
+  {
+    const int co = bd[3];
+    const __half *wc1 = L.hh("rb4k.c1.w", 3LL * co * 9 * 128), *wsc = L.hh("rb4k.sc.w", 3LL * co * 128), *wc2 = L.hh("rb4k.c2.w", 3LL * co * 9 * co);
+    const float *b1 = L.f("rb4k.c1.b", 3 * co), *b2 = L.f("rb4k.c2.b", 3 * co);
+    if (!L.ok) return MK_ERR_MISSING_TENSOR;
+    { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, 128, g.w2, true);
+      p.groups = 3; p.a_col_group_off = 256; p.b_row_group_off = co; p.bias = b1; p.bias_group_off = co; p.act = ACT_RELU;
+      p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_h = w.T4k; p.out_h_ld = 3 * co; p.out_h_group_off = co;
+      MK_TRY(gemm(h, EPI_CONV, w.CAT, g.R, G * 256, wc1, 3 * co, 9 * 128, p, st)); }
+    { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, 128, g.w2, false);
+      p.groups = 3; p.a_col_group_off = 256; p.b_row_group_off = co; p.out_h = w.S4k; p.out_h_ld = 3 * co; p.out_h_group_off = co;
+      MK_TRY(gemm(h, EPI_CONV, w.CAT, g.R, G * 256, wsc, 3 * co, 128, p, st)); }
+    { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, co, g.w2, true);
+      p.groups = 3; p.a_col_group_off = co; p.b_row_group_off = co; p.bias = b2; p.bias_group_off = co; p.act = ACT_RELU;
+      p.res_h = w.S4k; p.res_h_ld = 3 * co; p.res_h_group_off = co; p.pad_h2 = g.h2; p.pad_w2 = g.w2;
+      p.out_f = w.Y4k; p.out_f_ld = 3 * co; p.out_f_group_off = co;
+      MK_TRY(gemm(h, EPI_CONV, w.T4k, g.R, 3 * co, wc2, 3 * co, 9 * co, p, st)); }
+  }
+  {
+    const int co = c.desc_dim;
+    const __half *wc1 = L.hh("rb4d.c1.w", (long long)co * 9 * 128), *wc2 = L.hh("rb4d.c2.w", (long long)co * 9 * co);
+    const float *b1 = L.f("rb4d.c1.b", co), *b2 = L.f("rb4d.c2.b", co);
+    if (co != 128) { set_last_error("DSC_HEAD.LAST_DIM must be 128"); return MK_ERR_UNSUPPORTED; }
+    if (!L.ok) return MK_ERR_MISSING_TENSOR;
+    { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, 128, g.w2, true);
+      p.a_col_base = 3 * 256; p.bias = b1; p.act = ACT_RELU; p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_h = w.T4d; p.out_h_ld = co;
+      MK_TRY(gemm(h, EPI_CONV, w.CAT, g.R, G * 256, wc1, co, 9 * 128, p, st)); }
+    { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, co, g.w2, true);
+      p.bias = b2; p.act = ACT_NONE; p.res_h = w.CAT + 3 * 256; p.res_h_ld = G * 256;   // identity shortcut (in == out planes)
+      p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_f = w.Y4d; p.out_f_ld = co;
+      MK_TRY(gemm(h, EPI_CONV, w.T4d, g.R, co, wc2, co, 9 * co, p, st)); }
+  }
+  // -- output layers and activations
+  MK_TRY(kp_head_out(w.Y4k, L.f("out.depth.w", bd[3]), L.f("out.xy.w", 2 * bd[3]), L.f("out.score.w", bd[3]), depth, kps,
+                     w.score_raw, scr, g.n_img, g.gh, g.gw, c.depth_sigmoid, c.max_depth, (float)c.down_factor, c.use_softmax, st));
+  h->launches += 2;
+  if (!L.ok) return MK_ERR_MISSING_TENSOR;
+  if (bd[3] != 64) { set_last_error("KP_HEADS.BLOCKS_DIM[3] must be 64"); return MK_ERR_UNSUPPORTED; }
+  MK_TRY(desc_out(w.Y4d, dsc, w.DSCX, w.nrm2, g.n_img, g.gh, g.gw, c.norm_dsc, st)); h->launches++;
+  MK_CUDA_CHECK(cudaMemcpyAsync(w.scr_copy, scr, (size_t)g.n_img * g.N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return MK_OK;
+}
+
+// ---- stage 2 ----------------------------------------------------------------------------------------------
+int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores, float* final_scores, Workspace& w,
+              cudaStream_t st) {
+  const mk_config& c = h->cfg;
+  Lookup L{h};
+  const float* dust = c.use_dustbin ? L.f("dustbin", 1) : nullptr;
+  if (!L.ok) return MK_ERR_MISSING_TENSOR;
+  if (!scores || !kp_scores || !final_scores) {
+    set_last_error("mk_match: lean mode (NULL scores/kp_scores) is not implemented yet");
+    return MK_ERR_UNSUPPORTED;
+  }
+  const float inv_t = 1.0f / c.temperature;
+  MK_TRY(matcher_prep(w.nrm2, dust, inv_t, w.shift, w.row_sum, w.col_sum, n_pairs, N, st)); h->launches++;
+  const __half* A0 = w.DSCX;                                   // role-0 descriptors [n_pairs*N, 384]
+  const __half* A1 = w.DSCX + (size_t)n_pairs * N * 384;       // role-1 descriptors
+  const long long rows = (long long)n_pairs * N;
+  auto mp = [&]() {
+    GemmParams p = base_params(N, N, 384);
+    p.groups = n_pairs; p.a_row_group_off = N; p.b_row_group_off = N; p.n_valid = N; p.inv_temp = inv_t;
+    p.shift = w.shift; p.dustbin = dust;
+    return p;
+  };
+  { GemmParams p = mp(); p.row_sum = w.row_sum; MK_TRY(gemm(h, EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
+  { GemmParams p = mp(); p.row_sum = w.col_sum; MK_TRY(gemm(h, EPI_LSE, A1, rows, 384, A0, rows, 384, p, st)); }
+  { GemmParams p = mp(); p.rs = w.row_sum; p.cs = w.col_sum; p.scr0 = w.scr_copy; p.scr1 = w.scr_copy + (size_t)n_pairs * N;
+    p.scores = scores; p.kp_scores = kp_scores; p.final_scores = final_scores;
+    MK_TRY(gemm(h, EPI_DUAL, A0, rows, 384, A1, rows, 384, p, st)); }
+  return MK_OK;
+}
+
+// ---- stage 3 ----------------------------------------------------------------------------------------------
+int run_solve(mk_handle* h, const float* final_scores, const float* kps, const float* depth, const float* K0,
+              const float* K1, int n_pairs, int N, unsigned long long seed, const int* outer_idx, const int* inner_idx,
+              float* pose, int* best_set, float* inl_mask, int* sampled_out, float* hyp_scores_out, int* status_out,
+              Workspace& w, cudaStream_t st) {
+  const mk_config& c = h->cfg;
+  RansacParams rp{c.it_matches, c.it_ransac, c.num_sampled, c.num_corr, c.num_refine, c.th_inlier, c.th_soft_inlier, seed};
+  MK_CUDA_CHECK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
+  const size_t n_idx = (size_t)n_pairs * c.it_matches * c.num_sampled;
+  const int* idx = outer_idx;
+  if (!idx) {
+    MK_TRY(sample_outer(final_scores, n_pairs, N, c.it_matches, c.num_sampled, seed, w.samp_ws, w.idx, w.status, st));
+    h->launches += 4;
+    idx = w.idx;
+  }
+  const float* kps0 = kps;
+  const float* kps1 = kps + (size_t)n_pairs * 2 * N;
+  const float* d0 = depth;
+  const float* d1 = depth + (size_t)n_pairs * N;
+  int* bs = best_set ? best_set : w.best_hyp;     // scratch when the caller does not want it
+  MK_TRY(ransac_solve(final_scores, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.xyw, w.hyp_scores,
+                      w.hyp_Rt, w.status, pose, bs, inl_mask, best_set ? w.best_hyp : nullptr, st));
+  h->launches += 3;
+  if (sampled_out) MK_CUDA_CHECK(cudaMemcpyAsync(sampled_out, idx, n_idx * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (hyp_scores_out)
+    MK_CUDA_CHECK(cudaMemcpyAsync(hyp_scores_out, w.hyp_scores, (size_t)n_pairs * c.it_matches * c.it_ransac * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+  if (status_out) MK_CUDA_CHECK(cudaMemcpyAsync(status_out, w.status, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return MK_OK;
+}
+
+int check_ws(mk_handle* h, int n_pairs, int H, int W, void* ws, long long ws_bytes, Workspace& out) {
+  if (!h || !h->finalized) { set_last_error("handle not finalized"); return MK_ERR_INVALID; }
+  if (H != h->geo_h || W != h->geo_w) {
+    set_last_error("geometry %dx%d does not match the finalized geometry %dx%d", H, W, h->geo_h, h->geo_w);
+    return MK_ERR_INVALID;
+  }
+  const Geo g = make_geo(n_pairs, H, W);
+  out = carve(ws, h->cfg, g, n_pairs);
+  if (!ws || (long long)out.bytes > ws_bytes) {
+    set_last_error("workspace too small: need %zu bytes, got %lld", out.bytes, ws_bytes);
+    return MK_ERR_INVALID;
+  }
+  return MK_OK;
+}
+
+}  // namespace
+
+// ============================================================================================================
+extern "C" {
+
+const char* mk_last_error(void) { return mk::last_error(); }
+const char* mk_version(void) { return "mickey_b200 0.1.0 (sm_100a)"; }
+int mk_sizeof_config(void) { return (int)sizeof(mk_config); }
+int mk_sizeof_gemm_args(void) { return (int)sizeof(mk_gemm_args); }
+
+int mk_create(int device, const mk_config* cfg, mk_handle** out) {
+  if (!cfg || !out) { set_last_error("null argument"); return MK_ERR_INVALID; }
+  if (cfg->embed_dim != cfg->heads * 64 || cfg->embed_dim % 128) {
+    set_last_error("unsupported backbone: embed_dim %d heads %d", cfg->embed_dim, cfg->heads);
+    return MK_ERR_UNSUPPORTED;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    set_last_error("CUDA device %d not available (a B200 is required; there is no CPU path)", device);
+    return MK_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  MK_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    return MK_ERR_UNSUPPORTED;
+  }
+  mk_handle* h = new mk_handle();
+  h->device = device;
+  h->cfg = *cfg;
+  *out = h;
+  return MK_OK;
+}
+
+int mk_destroy(mk_handle* h) { delete h; return MK_OK; }
+
+int mk_set_tensor(mk_handle* h, const char* name, const void* ptr, int dtype, long long numel) {
+  if (!h || !name || !ptr) { set_last_error("null argument"); return MK_ERR_INVALID; }
+  h->tensors[name] = Tensor{ptr, dtype, numel};
+  return MK_OK;
+}
+
+int mk_finalize(mk_handle* h, int H, int W) {
+  if (!h) return MK_ERR_INVALID;
+  if (H < 14 * 7 || W < 14 * 7) { set_last_error("image %dx%d too small (3-px border mask needs >= 7 cells)", H, W); return MK_ERR_INVALID; }
+  h->geo_h = H; h->geo_w = W; h->finalized = true;
+  return MK_OK;
+}
+
+long long mk_workspace_bytes(mk_handle* h, int n_pairs, int H, int W) {
+  if (!h) return -1;
+  const Geo g = make_geo(n_pairs, H, W);
+  return (long long)carve(nullptr, h->cfg, g, n_pairs).bytes;
+}
+
+int mk_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, float* kps, float* depth, float* scr,
+               float* dsc, void* ws, long long ws_bytes, void* stream) {
+  Workspace w;
+  MK_TRY(check_ws(h, n_pairs, H, W, ws, ws_bytes, w));
+  return run_extract(h, images, n_pairs, H, W, kps, depth, scr, dsc, w, (cudaStream_t)stream);
+}
+
+int mk_match(mk_handle* h, int n_pairs, float* scores, float* kp_scores, float* final_scores, void* ws,
+             long long ws_bytes, void* stream) {
+  Workspace w;
+  MK_TRY(check_ws(h, n_pairs, h ? h->geo_h : 0, h ? h->geo_w : 0, ws, ws_bytes, w));
+  const Geo g = make_geo(n_pairs, h->geo_h, h->geo_w);
+  return run_match(h, n_pairs, g.N, scores, kp_scores, final_scores, w, (cudaStream_t)stream);
+}
+
+int mk_solve_pose(mk_handle* h, const float* final_scores, const float* kps, const float* depth, const float* K0,
+                  const float* K1, int n_pairs, int n_kpts, unsigned long long seed, const int* outer_idx,
+                  const int* inner_idx, float* pose, int* best_set, float* inl_mask, int* sampled_out,
+                  float* hyp_scores_out, int* status, void* ws, long long ws_bytes, void* stream) {
+  Workspace w;
+  MK_TRY(check_ws(h, n_pairs, h ? h->geo_h : 0, h ? h->geo_w : 0, ws, ws_bytes, w));
+  const Geo g = make_geo(n_pairs, h->geo_h, h->geo_w);
+  if (n_kpts != g.N) { set_last_error("n_kpts %d does not match the geometry (%d)", n_kpts, g.N); return MK_ERR_INVALID; }
+  return run_solve(h, final_scores, kps, depth, K0, K1, n_pairs, n_kpts, seed, outer_idx, inner_idx, pose, best_set,
+                   inl_mask, sampled_out, hyp_scores_out, status, w, (cudaStream_t)stream);
+}
+
+int mk_forward(mk_handle* h, const float* images, const float* K0, const float* K1, int n_pairs, int H, int W,
+               unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
+               float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
+               int* status, void* ws, long long ws_bytes, void* stream) {
+  Workspace w;
+  MK_TRY(check_ws(h, n_pairs, H, W, ws, ws_bytes, w));
+  const Geo g = make_geo(n_pairs, H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  MK_TRY(run_extract(h, images, n_pairs, H, W, kps, depth, scr, dsc, w, st));
+  MK_TRY(run_match(h, n_pairs, g.N, scores, kp_scores, final_scores, w, st));
+  return run_solve(h, final_scores, kps, depth, K0, K1, n_pairs, g.N, seed, nullptr, nullptr, pose, best_set, inl_mask,
+                   sampled_out, nullptr, status, w, st);
+}
+
+long long mk_launch_count(mk_handle* h) { return h ? h->launches : -1; }
+
+// ---- operator-level entry points ---------------------------------------------------------------------------------
+int mk_op_gemm(const mk_gemm_args* a, void* stream) {
+  if (!a) return MK_ERR_INVALID;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.k_chunks = a->k_chunks; p.chunks_per_tap = a->chunks_per_tap; p.num_taps = a->num_taps;
+  for (int i = 0; i < 9; ++i) p.tap_shift[i] = a->tap_shift[i];
+  p.groups = a->groups; p.a_row_group_off = a->a_row_group_off; p.a_col_group_off = a->a_col_group_off;
+  p.a_col_base = a->a_col_base; p.b_row_group_off = a->b_row_group_off; p.act = a->act;
+  p.bias = a->bias; p.bias_group_off = a->bias_group_off; p.gamma = a->gamma; p.beta = a->beta; p.ln_group_off = a->ln_group_off;
+  p.out_f = a->out_f; p.out_f_ld = a->out_f_ld; p.out_f_group_off = a->out_f_group_off;
+  p.out_h = (__half*)a->out_h; p.out_h_ld = a->out_h_ld; p.out_h_group_off = a->out_h_group_off;
+  p.res_h = (const __half*)a->res_h; p.res_h_ld = a->res_h_ld; p.res_h_group_off = a->res_h_group_off;
+  p.aux = a->aux; p.aux_group_mask = a->aux_group_mask; p.pad_h2 = a->pad_h2; p.pad_w2 = a->pad_w2; p.tok_per_img = a->tok_per_img;
+  p.eps = a->eps; p.n_valid = a->n_valid; p.inv_temp = a->inv_temp; p.shift = a->shift; p.dustbin = a->dustbin;
+  p.row_sum = a->row_sum; p.rs = a->rs; p.cs = a->cs; p.scr0 = a->scr0; p.scr1 = a->scr1;
+  p.scores = a->scores; p.kp_scores = a->kp_scores; p.final_scores = a->final_scores;
+  GemmOperand A{a->a, a->a_rows, a->a_cols, a->a_ld}, B{a->b, a->b_rows, a->b_cols, a->b_ld};
+  return launch_gemm(a->epi, A, B, p, (cudaStream_t)stream, a->impl);
+}
+
+int mk_op_patch_gather(const float* img, void* P, int n_img, int H, int W, int kpad, float* X, const float* cls_pos,
+                       int D, void* stream) {
+  return patch_gather(img, P, n_img, H, W, kpad, X, cls_pos, D, (cudaStream_t)stream);
+}
+int mk_op_layernorm(const float* x, const float* w, const float* b, void* out, int rows, int D, float eps, int mode,
+                    int gh, int gw, void* stream) {
+  return layernorm(x, w, b, out, rows, D, eps, mode, gh, gw, (cudaStream_t)stream);
+}
+int mk_op_attention(const void* qkv, void* out, int n_img, int T, int D, int heads, void* stream) {
+  return attention(qkv, out, n_img, T, D, heads, (cudaStream_t)stream);
+}
+int mk_op_linattn(const float* qkv, float* kv, void* msg, int n_img, int Gn, int h2, int w2, float eps, void* stream) {
+  MK_TRY(linattn_kv(qkv, kv, n_img, Gn, h2, w2, (cudaStream_t)stream));
+  return linattn_msg(qkv, kv, msg, n_img, Gn, h2, w2, eps, (cudaStream_t)stream);
+}
+long long mk_op_sample_workspace_bytes(int B, int IM) { return (long long)sampler_workspace_bytes(B, IM); }
+int mk_op_sample(const float* fs, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
+                 long long ws_bytes, int* idx_out, int* status, void* stream) {
+  if ((long long)sampler_workspace_bytes(B, IM) > ws_bytes) { set_last_error("sampler workspace too small"); return MK_ERR_INVALID; }
+  MK_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), (cudaStream_t)stream));
+  return sample_outer(fs, B, N, IM, n_sample, seed, ws, idx_out, status, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+// Host side of the GEMM family: TMA descriptor encoding, launch dispatch, and the SIMT debug kernel.
+#include "gemm.h"
+#include "gemm_tc.cuh"
+
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+namespace mk {
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed) ---------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// Descriptors are pure functions of (pointer, shape, box); the engine reuses the same workspace and
+// weight buffers every call, so they are cached.
+struct MapKey {
+  const void* ptr; long long rows, cols, ld; int box;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols; h = h * 1000003u ^ (size_t)k.ld;
+    return h * 1000003u ^ (size_t)k.box;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static std::mutex g_map_mutex;
+
+static int encode_tensor_map_f16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld_elems,
+                                 int box_rows);
+
+int make_tensor_map_f16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld_elems,
+                        int box_rows) {
+  MapKey key{ptr, rows, cols, ld_elems, box_rows};
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) { *map = it->second; return MK_OK; }
+  int rc = encode_tensor_map_f16(map, ptr, rows, cols, ld_elems, box_rows);
+  if (rc == MK_OK) {
+    if (g_map_cache.size() > 4096) g_map_cache.clear();
+    g_map_cache.emplace(key, *map);
+  }
+  return rc;
+}
+
+static int encode_tensor_map_f16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld_elems,
+                                 int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MK_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld_elems % 8)) {
+    set_last_error("tensor map operand must be 16-byte aligned with ld %% 8 == 0 (ptr=%p ld=%lld)", ptr, ld_elems);
+    return MK_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return MK_ERR_CUDA; }
+  return MK_OK;
+}
+
+// ---- SIMT debug kernel --------------------------------------------------------------------------------
+// Same operand addressing and the same epilogues as the tcgen05 kernel, computed with plain FFMA.  It is
+// NOT a product path: it exists so that a GPU test can tell a tcgen05/TMA descriptor bug from an epilogue
+// bug (tests/test_gpu_ops.py runs both and compares), selectable with MICKEY_GEMM_IMPL=simt.
+template <int BN, int EPI>
+__global__ void __launch_bounds__(128)
+gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, const __half* __restrict__ B,
+                 long long b_rows, long long ldb, const GemmParams p) {
+  __shared__ __half As[BLOCK_M][BLOCK_K + 8];
+  __shared__ __half Bs[BN][BLOCK_K + 8];
+  const int g = blockIdx.z, m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BN;
+  const int t = threadIdx.x;
+  float acc[BN];
+#pragma unroll
+  for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+  const int a_col0 = p.a_col_base + g * p.a_col_group_off;
+  const long long a_row0 = (long long)m0 + (long long)g * p.a_row_group_off;
+  const long long b_row0 = (long long)n0 + (long long)g * p.b_row_group_off;
+  for (int kc = 0; kc < p.k_chunks; ++kc) {
+    const int tap = kc / p.chunks_per_tap, kin = kc - tap * p.chunks_per_tap;
+    for (int idx = t; idx < BLOCK_M * BLOCK_K; idx += 128) {
+      const int r = idx / BLOCK_K, c = idx % BLOCK_K;
+      const long long row = a_row0 + r + p.tap_shift[tap];
+      const long long col = a_col0 + kin * BLOCK_K + c;
+      As[r][c] = (row >= 0 && row < a_rows && col < lda) ? A[row * lda + col] : __float2half(0.f);
+    }
+    for (int idx = t; idx < BN * BLOCK_K; idx += 128) {
+      const int r = idx / BLOCK_K, c = idx % BLOCK_K;
+      const long long row = b_row0 + r;
+      Bs[r][c] = (row < b_rows) ? B[row * ldb + (long long)kc * BLOCK_K + c] : __float2half(0.f);
+    }
+    __syncthreads();
+    for (int k = 0; k < BLOCK_K; ++k) {
+      const float a = __half2float(As[t][k]);
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = fmaf(a, __half2float(Bs[j][k]), acc[j]);
+    }
+    __syncthreads();
+  }
+  const int m = m0 + t;
+  float v[32];
+  if constexpr (EPI == EPI_LN) {
+    float sum = 0.f;
+    for (int j = 0; j < BN; ++j) sum += acc[j];
+    const float mean = sum / BN;
+    float sq = 0.f;
+    for (int j = 0; j < BN; ++j) { const float d = acc[j] - mean; sq += d * d; }
+    const float rstd = rsqrtf(sq / BN + p.eps);
+    for (int c = 0; c < BN / 32; ++c) {
+      for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
+      ln_store_chunk(p, g, m, n0 + c * 32, v, mean, rstd);
+    }
+  } else if constexpr (EPI == EPI_LSE) {
+    float s = 0.f;
+    for (int c = 0; c < BN / 32; ++c) {
+      for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
+      s += lse_partial(p, g, n0 + c * 32, v);
+    }
+    if (m < p.n_valid) atomicAdd(p.row_sum + (size_t)g * p.n_valid + m, s);
+  } else {
+    for (int c = 0; c < BN / 32; ++c) {
+      if (n0 + c * 32 < p.N) {
+        for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
+        epilogue_chunk<EPI>(p, g, m, n0 + c * 32, v);
+      }
+    }
+  }
+}
+
+// ---- dispatch -----------------------------------------------------------------------------------------
+static bool use_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MICKEY_GEMM_IMPL");
+    v = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int BN, int EPI>
+static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmParams& p, cudaStream_t stream, int impl) {
+  dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(p.N, BN), p.groups);
+  if (impl == GEMM_IMPL_SIMT) {
+    gemm_simt_kernel<BN, EPI><<<grid, 128, 0, stream>>>(reinterpret_cast<const __half*>(A.ptr), A.rows, A.ld,
+                                                          reinterpret_cast<const __half*>(B.ptr), B.rows, B.ld, p);
+  } else {
+    static bool attr_set = false;
+    constexpr int smem = gemm_smem_bytes<BN>();
+    if (!attr_set) {
+      MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    int rc = make_tensor_map_f16(&tmA, A.ptr, A.rows, A.cols, A.ld, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tensor_map_f16(&tmB, B.ptr, B.rows, B.cols, B.ld, BN);
+    if (rc) return rc;
+    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+  }
+  MK_CUDA_CHECK(cudaGetLastError());
+  return MK_OK;
+}
+
+template <int EPI>
+static int launch_bn(int bn, const GemmOperand& A, const GemmOperand& B, const GemmParams& p, cudaStream_t s, int impl) {
+  if (bn == 128) return launch_one<128, EPI>(A, B, p, s, impl);
+  if (bn == 64) return launch_one<64, EPI>(A, B, p, s, impl);
+  set_last_error("unsupported BLOCK_N %d", bn);
+  return MK_ERR_INVALID;
+}
+
+int launch_gemm(int epi, const GemmOperand& A, const GemmOperand& B, const GemmParams& p, cudaStream_t stream, int impl) {
+  if (impl == GEMM_IMPL_DEFAULT) impl = use_simt() ? GEMM_IMPL_SIMT : GEMM_IMPL_TC;
+  if (p.k_chunks <= 0 || p.M <= 0 || p.N <= 0 || p.groups <= 0) { set_last_error("bad GEMM shape"); return MK_ERR_INVALID; }
+  const bool matcher = (epi == EPI_LSE || epi == EPI_DUAL);
+  if (!matcher && (p.N % 32)) { set_last_error("GEMM N=%d must be a multiple of 32", p.N); return MK_ERR_INVALID; }
+  int bn = (matcher || p.N % 128 == 0) ? 128 : 64;
+  if (!matcher && p.N % bn) { set_last_error("GEMM N=%d not tileable", p.N); return MK_ERR_INVALID; }
+  if (epi == EPI_LN && p.N != 128) { set_last_error("EPI_LN needs N == 128"); return MK_ERR_INVALID; }
+  switch (epi) {
+    case EPI_STORE_H: return launch_bn<EPI_STORE_H>(bn, A, B, p, stream, impl);
+    case EPI_RESID_F: return launch_bn<EPI_RESID_F>(bn, A, B, p, stream, impl);
+    case EPI_PATCH:   return launch_bn<EPI_PATCH>(bn, A, B, p, stream, impl);
+    case EPI_CONV:    return launch_bn<EPI_CONV>(bn, A, B, p, stream, impl);
+    case EPI_STORE_F: return launch_bn<EPI_STORE_F>(bn, A, B, p, stream, impl);
+    case EPI_LN:      return launch_one<128, EPI_LN>(A, B, p, stream, impl);
+    case EPI_LSE:     return launch_one<128, EPI_LSE>(A, B, p, stream, impl);
+    case EPI_DUAL:    return launch_one<128, EPI_DUAL>(A, B, p, stream, impl);
+  }
+  set_last_error("unknown epilogue %d", epi);
+  return MK_ERR_INVALID;
+}
+
+// ---- error string -------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+}  // namespace mk

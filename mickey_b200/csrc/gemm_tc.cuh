@@ -1,0 +1,268 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+//   D[M,N] (fp32 in TMEM) = A[M,K] * B[N,K]^T,   A and B fp16, K-major, 128-byte swizzled tiles
+//
+// CTA = one 128 x BN output tile.  Warp roles (256 threads):
+//   warp 0  : TMA producer   (one elected lane issues cp.async.bulk.tensor.2d into the smem ring)
+//   warp 1  : MMA issuer     (one elected lane issues tcgen05.mma, commits to the ring's empty barriers)
+//   warp 2  : TMEM allocator (tcgen05.alloc / dealloc of BN fp32 columns)
+//   warp 3  : idle
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b: thread == output row, 32 columns per load)
+// Two CTAs are resident per SM (3-stage ring, <= 128 TMEM columns each) so one CTA's epilogue
+// overlaps the other's main loop.
+//
+// The K loop walks `k_chunks` 64-element chunks.  For convolutions a chunk also selects a filter tap:
+// the A tile of tap t is the same 2-D tensor read at row offset tap_shift[t] (negative / overflowing
+// rows are zero-filled by TMA), which turns a 3x3 convolution over a zero-padded NHWC image into 9
+// accumulated GEMMs without materialising im2col.
+#pragma once
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace mk {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;        // 64 fp16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+constexpr int gemm_smem_bytes() {
+  return GEMM_STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row groups
+// 1024 bytes apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 bytes
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::f16: D fp32, A/B fp16, both K-major, M=128, N=BN
+// (cute::UMMA::InstrDescriptor: c_format [4,6)=1, a/b_format=0, n_dim=N>>3 [17,23), m_dim=M>>4 [24,29)).
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16() {
+  return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// ---- kernel ------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_BYTES = BN * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle-128B tiles need 1024-byte alignment
+  const uint32_t bar_base = base + GEMM_STAGES * STAGE_BYTES;   // full[S], empty[S], tmem_full, tmem_ptr
+  const uint32_t full_bar0 = bar_base;
+  const uint32_t empty_bar0 = bar_base + 8 * GEMM_STAGES;
+  const uint32_t tmem_full_bar = bar_base + 16 * GEMM_STAGES;
+  const uint32_t tmem_ptr_addr = bar_base + 16 * GEMM_STAGES + 8;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.z;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(full_bar0 + 8 * s, 1);
+      mbar_init(empty_bar0 + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int a_col0 = p.a_col_base + g * p.a_col_group_off;
+      const int a_row0 = m0 + g * p.a_row_group_off;
+      const int b_row0 = n0 + g * p.b_row_group_off;
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int tap = kc / p.chunks_per_tap;
+        const int kin = kc - tap * p.chunks_per_tap;
+        mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = base + stage * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const uint32_t fb = full_bar0 + 8 * stage;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        tma_load_2d(sa, &tmA, fb, a_col0 + kin * BLOCK_K, a_row0 + p.tap_shift[tap]);
+        tma_load_2d(sb, &tmB, fb, kc * BLOCK_K, b_row0);
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    constexpr uint32_t idesc = umma_idesc_f16<BN>();
+    for (int kc = 0; kc < p.k_chunks; ++kc) {
+      mbar_wait(full_bar0 + 8 * stage, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = base + stage * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const uint64_t da = umma_desc_sw128(sa);
+        const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar0 + 8 * stage);                   // frees this smem stage when the MMAs retire
+        if (kc == p.k_chunks - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float v[32];
+    if constexpr (EPI == EPI_LN) {
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += v[j];
+      }
+      const float mean = sum * (1.0f / BN);
+      float sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq += d * d; }
+      }
+      const float rstd = rsqrtf(sq * (1.0f / BN) + p.eps);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(taddr + c * 32, v);
+        ln_store_chunk(p, g, m, n0 + c * 32, v, mean, rstd);
+      }
+    } else if constexpr (EPI == EPI_LSE) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(taddr + c * 32, v);
+        s += lse_partial(p, g, n0 + c * 32, v);
+      }
+      if (m < p.n_valid) atomicAdd(p.row_sum + (size_t)g * p.n_valid + m, s);
+    } else {
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 < p.N) {
+          tmem_ld32(taddr + c * 32, v);
+          epilogue_chunk<EPI>(p, g, m, n0 + c * 32, v);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+}  // namespace mk

@@ -1,0 +1,618 @@
+// Probabilistic Procrustes RANSAC (reference modules/utils/probabilisticProcrustes.py:183-348).
+//
+//  1. outer sampling  : IT_MATCHES x "2048 of N*N cells without replacement, prob ~ final_scores".
+//                       ATen's multinomial is top-k of p / Exp(1) (an exponential race); we run the same race
+//                       with a counter-based generator (Philox4x32-10) so that each pass can regenerate the
+//                       noise instead of materialising the [B*IT_MATCHES, N*N] tile the reference allocates:
+//                       pass A histograms the keys (8 exponent + 3 mantissa bits), a scan finds the bin holding
+//                       the 2048-th largest key, pass B collects the <= ~2.3 k candidates at/above it, pass C
+//                       sorts them (key desc, cell index as tie-break) and keeps the first 2048.
+//  2. gather          : cell -> (keypoint i0, keypoint i1), back-projection X = d * K^-1 [u v 1]^T   (training_utils.py:7-22)
+//  3. hypotheses      : IT_RANSAC x (3 of 2048 without replacement ~ weight; Kabsch via 3x3 one-sided Jacobi SVD;
+//                       soft inlier score over the set's 2048 correspondences)                  (solvers.py:3-54, training_utils.py:55-61)
+//  4. finalize        : argmax, <= NUM_REFINEMENTS masked-Kabsch refinements on hard inliers, final soft count.
+#include "ops.h"
+
+namespace mk {
+
+// ---- Philox4x32-10 -------------------------------------------------------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(unsigned long long seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// Exp(1) variate with full relative precision near 0 (small E decides the race): E = -log1p(-u), u in (0,1)
+__device__ __forceinline__ float exp1_from_bits(uint32_t x) {
+  const float u = fminf(((float)x + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
+  return (u < 0.01f) ? u * (1.0f + u * (0.5f + u * (0.33333334f + 0.25f * u))) : -__logf(1.0f - u);
+}
+__device__ __forceinline__ float u01_from_bits(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+
+__device__ __forceinline__ uint32_t race_key(float p, uint32_t bits) {
+  return (p > 0.f) ? __float_as_uint(p / exp1_from_bits(bits)) : 0u;
+}
+
+constexpr int HBINS = 2048;          // key >> 20 (sign is always 0)
+constexpr int SAMP_THREADS = 256;
+constexpr int SAMP_ELEMS_PER_BLOCK = 256 * 32;
+
+// ---- pass A: histogram ------------------------------------------------------------------------------------
+// grid (blocks over N*N, ceil(IM/4), B); one Philox call per cell yields the noise of 4 streams.
+__global__ void __launch_bounds__(SAMP_THREADS)
+sampler_hist_kernel(const float* __restrict__ fs, long long cells, int IM, unsigned long long seed,
+                    unsigned int* __restrict__ hist) {
+  __shared__ unsigned int h[4][HBINS];
+  for (int i = threadIdx.x; i < 4 * HBINS; i += SAMP_THREADS) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const int sg = blockIdx.y, b = blockIdx.z;
+  const float* p = fs + (long long)b * cells;
+  const Philox rng(seed);
+  const long long e0 = (long long)blockIdx.x * SAMP_ELEMS_PER_BLOCK;
+  const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
+  for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) {
+    const float pv = p[e];
+    if (pv > 0.f) {
+      const uint4 r = rng((uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)sg, (uint32_t)b);
+      atomicAdd(&h[0][race_key(pv, r.x) >> 20], 1u);
+      atomicAdd(&h[1][race_key(pv, r.y) >> 20], 1u);
+      atomicAdd(&h[2][race_key(pv, r.z) >> 20], 1u);
+      atomicAdd(&h[3][race_key(pv, r.w) >> 20], 1u);
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < 4; ++j) {
+    const int s = sg * 4 + j;
+    if (s >= IM) break;
+    unsigned int* dst = hist + ((long long)b * IM + s) * HBINS;
+    for (int i = threadIdx.x; i < HBINS; i += SAMP_THREADS)
+      if (h[j][i]) atomicAdd(dst + i, h[j][i]);
+  }
+}
+
+// threshold bin per stream: largest T with count(bin >= T) >= n_sample.  one warp per stream.
+__global__ void sampler_threshold_kernel(const unsigned int* __restrict__ hist, int n_streams, int n_sample,
+                                         int* __restrict__ thr, int* __restrict__ status) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= n_streams) return;
+  const unsigned int* h = hist + (long long)s * HBINS;
+  unsigned int above = 0;
+  int T = -1;
+  for (int base = HBINS - 32; base >= 0 && T < 0; base -= 32) {
+    const unsigned int c = h[base + lane];
+    // inclusive suffix sum within the 32 bins (lane 31 = highest bin)
+    unsigned int suf = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += v;
+    }
+    const unsigned int tot = __shfl_sync(0xffffffffu, suf, 0);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, above + suf >= (unsigned)n_sample);
+    if (ballot) {
+      T = base + (31 - __clz(ballot));     // highest bin whose suffix count reaches n_sample
+    } else {
+      above += tot;
+    }
+  }
+  if (lane == 0) {
+    // bin 0 holds the zero-probability cells (key 0): they may never be drawn (ATen raises in that case and
+    // the reference's try/except returns the zero pose, probabilisticProcrustes.py:331-342)
+    if (T <= 0) { T = 1; atomicOr(status, 1); }
+    thr[s] = T;
+  }
+}
+
+// ---- pass B: collect candidates (bin >= threshold) ---------------------------------------------------------
+__global__ void __launch_bounds__(SAMP_THREADS)
+sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, unsigned long long seed,
+                       const int* __restrict__ thr, unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt,
+                       int cap) {
+  const int sg = blockIdx.y, b = blockIdx.z;
+  const float* p = fs + (long long)b * cells;
+  const Philox rng(seed);
+  int T[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) T[j] = (sg * 4 + j < IM) ? thr[(long long)b * IM + sg * 4 + j] : 0x7fffffff;
+  const long long e0 = (long long)blockIdx.x * SAMP_ELEMS_PER_BLOCK;
+  const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
+  for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) {
+    const float pv = p[e];
+    if (pv > 0.f) {
+      const uint4 r = rng((uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)sg, (uint32_t)b);
+      const uint32_t k[4] = {race_key(pv, r.x), race_key(pv, r.y), race_key(pv, r.z), race_key(pv, r.w)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((int)(k[j] >> 20) >= T[j]) {
+          const long long s = (long long)b * IM + sg * 4 + j;
+          const unsigned int slot = atomicAdd(cnt + s, 1u);
+          if (slot < (unsigned)cap) cand[s * cap + slot] = ((unsigned long long)k[j] << 32) | (uint32_t)e;
+        }
+      }
+    }
+  }
+}
+
+// ---- pass C: sort candidates, keep the n_sample largest -----------------------------------------------------
+template <int CAP>
+__global__ void __launch_bounds__(1024)
+sampler_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, int n_sample,
+                      int* __restrict__ idx_out, int* __restrict__ status) {
+  extern __shared__ unsigned long long keys[];
+  const long long s = blockIdx.x;
+  const unsigned int n_raw = cnt[s];
+  const int n = (int)min(n_raw, (unsigned)CAP);
+  if (threadIdx.x == 0) {
+    if (n_raw > (unsigned)CAP) atomicOr(status, 2);     // candidate buffer overflow (selection truncated)
+    if (n < n_sample) atomicOr(status, 1);
+  }
+  for (int i = threadIdx.x; i < CAP; i += 1024) keys[i] = (i < n) ? cand[s * CAP + i] : 0ull;
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= CAP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < CAP; i += 1024) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], c = keys[ixj];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n_sample; i += 1024) idx_out[s * n_sample + i] = (int)(uint32_t)keys[i];
+}
+
+constexpr int CAND_CAP = 8192;
+
+size_t sampler_workspace_bytes(int B, int IM) {
+  const size_t streams = (size_t)B * IM;
+  return streams * HBINS * 4 + streams * 4 /*thr*/ + streams * 4 /*cnt*/ + streams * CAND_CAP * 8 + 256;
+}
+
+int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
+                 int* idx_out, int* status, cudaStream_t st) {
+  if (n_sample > CAND_CAP / 2) { set_last_error("NUM_SAMPLED_MATCHES %d too large", n_sample); return MK_ERR_UNSUPPORTED; }
+  const long long cells = (long long)N * N;
+  const size_t streams = (size_t)B * IM;
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(w); w += streams * HBINS * 4;
+  int* thr = reinterpret_cast<int*>(w); w += streams * 4;
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(w); w += streams * 4;
+  w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w) + 255) & ~(uintptr_t)255);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(w);
+  MK_CUDA_CHECK(cudaMemsetAsync(hist, 0, streams * HBINS * 4 + streams * 8, st));
+  dim3 grid((unsigned)((cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK), ceil_div(IM, 4), B);
+  sampler_hist_kernel<<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, hist);
+  MK_CUDA_CHECK(cudaGetLastError());
+  sampler_threshold_kernel<<<ceil_div((int)streams, 4), 128, 0, st>>>(hist, (int)streams, n_sample, thr, status);
+  MK_CUDA_CHECK(cudaGetLastError());
+  sampler_collect_kernel<<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, cand, cnt, CAND_CAP);
+  MK_CUDA_CHECK(cudaGetLastError());
+  static bool attr = false;
+  if (!attr) {
+    MK_CUDA_CHECK(cudaFuncSetAttribute(sampler_select_kernel<CAND_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
+    attr = true;
+  }
+  sampler_select_kernel<CAND_CAP><<<(unsigned)streams, 1024, CAND_CAP * 8, st>>>(cand, cnt, n_sample, idx_out, status);
+  MK_CUDA_CHECK(cudaGetLastError());
+  return MK_OK;
+}
+
+// ---- gather + back-projection ----------------------------------------------------------------------------------
+__device__ __forceinline__ void inv3x3(const float* K, float* Ki) {
+  const double a = K[0], b = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i = K[8];
+  const double A = e * i - f * h, Bc = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + b * Bc + c * C;
+  const double id = 1.0 / det;
+  Ki[0] = (float)(A * id);  Ki[1] = (float)(-(b * i - c * h) * id); Ki[2] = (float)((b * f - c * e) * id);
+  Ki[3] = (float)(Bc * id); Ki[4] = (float)((a * i - c * g) * id);  Ki[5] = (float)(-(a * f - c * d) * id);
+  Ki[6] = (float)(C * id);  Ki[7] = (float)(-(a * h - b * g) * id); Ki[8] = (float)((a * e - b * d) * id);
+}
+
+// xyw [B*IM, 8, n_s] (SoA: X0 X1 X2 Y0 Y1 Y2 w pad)
+__global__ void ransac_gather_kernel(const int* __restrict__ idx, const float* __restrict__ fs,
+                                     const float* __restrict__ kps0, const float* __restrict__ d0,
+                                     const float* __restrict__ kps1, const float* __restrict__ d1,
+                                     const float* __restrict__ K0, const float* __restrict__ K1, int N, int IM, int n_s,
+                                     float* __restrict__ xyw) {
+  const int s = blockIdx.x, b = s / IM;
+  __shared__ float Ki0[9], Ki1[9];
+  if (threadIdx.x == 0) { inv3x3(K0 + b * 9, Ki0); inv3x3(K1 + b * 9, Ki1); }
+  __syncthreads();
+  float* o = xyw + (long long)s * 8 * n_s;
+  for (int i = threadIdx.x; i < n_s; i += blockDim.x) {
+    const int cell = idx[(long long)s * n_s + i];
+    const int i0 = cell / N, i1 = cell - i0 * N;
+    const float u0 = kps0[((long long)b * 2 + 0) * N + i0], v0 = kps0[((long long)b * 2 + 1) * N + i0];
+    const float u1 = kps1[((long long)b * 2 + 0) * N + i1], v1 = kps1[((long long)b * 2 + 1) * N + i1];
+    const float z0 = d0[(long long)b * N + i0], z1 = d1[(long long)b * N + i1];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      o[r * n_s + i] = z0 * (Ki0[r * 3] * u0 + Ki0[r * 3 + 1] * v0 + Ki0[r * 3 + 2]);
+      o[(3 + r) * n_s + i] = z1 * (Ki1[r * 3] * u1 + Ki1[r * 3 + 1] * v1 + Ki1[r * 3 + 2]);
+    }
+    o[6 * n_s + i] = fs[(long long)b * N * N + cell];
+  }
+}
+
+// ---- 3x3 SVD (one-sided Jacobi, fp64) and Kabsch ------------------------------------------------------------------
+// H = U S V^T.  Returns R = V diag(1,1,det(U V^T)) U^T (solvers.py:45-50).  With u3 := u1 x u2 and v3 := v1 x v2 both
+// factors are proper rotations, so R = V U^T already has det +1 and equals the reference's sign-fixed product for
+// every rank >= 2 matrix (3-point hypotheses are always rank <= 2: the third singular direction is a cross product,
+// not a division by ~0).
+__device__ void kabsch_rotation(const double* Hin, double* R) {
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A[i][j] = Hin[i * 3 + j];
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
+      double al = 0, be = 0, ga = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { al += A[i][p] * A[i][p]; be += A[i][q] * A[i][q]; ga += A[i][p] * A[i][q]; }
+      const double lim = 1e-15 * sqrt(al * be);
+      if (fabs(ga) > lim && fabs(ga) > 1e-300) {
+        off = fmax(off, fabs(ga) / fmax(sqrt(al * be), 1e-300));
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double ap = A[i][p], aq = A[i][q];
+          A[i][p] = c * ap - s * aq; A[i][q] = s * ap + c * aq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
+        }
+      }
+    }
+    if (off < 1e-14) break;
+  }
+  double sg[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) sg[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+  int i1 = 0;
+  if (sg[1] > sg[i1]) i1 = 1;
+  if (sg[2] > sg[i1]) i1 = 2;
+  int i2 = (i1 + 1) % 3, i3 = (i1 + 2) % 3;
+  if (sg[i3] > sg[i2]) { const int tmp = i2; i2 = i3; i3 = tmp; }
+  double u1[3], u2[3], v1[3], v2[3];
+  const double s1 = sg[i1], s2 = sg[i2];
+  if (!(s1 > 0.0)) {     // H == 0 (or NaN): identity (NaN inputs propagate through t and are flagged by the caller)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (s1 != s1) R[0] = s1;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { u1[i] = A[i][i1] / s1; v1[i] = V[i][i1]; v2[i] = V[i][i2]; }
+  if (s2 > 1e-14 * s1) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u2[i] = A[i][i2] / s2;
+    // re-orthogonalise u2 against u1 (guards the nearly rank-1 case)
+    const double d = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+    double nn = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { u2[i] -= d * u1[i]; nn += u2[i] * u2[i]; }
+    nn = 1.0 / sqrt(nn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u2[i] *= nn;
+  } else {
+    // rank 1 (collinear sample): the optimum is not unique; pick the completion that maps v2 -> any unit vector
+    // orthogonal to u1 (the reference's LAPACK choice is equally arbitrary)
+    int k = 0;
+    if (fabs(u1[1]) < fabs(u1[k])) k = 1;
+    if (fabs(u1[2]) < fabs(u1[k])) k = 2;
+    double e[3] = {0, 0, 0};
+    e[k] = 1.0;
+    const double d = u1[k];
+    double nn = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { u2[i] = e[i] - d * u1[i]; nn += u2[i] * u2[i]; }
+    nn = 1.0 / sqrt(nn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u2[i] *= nn;
+  }
+  const double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+  const double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = v1[i] * u1[j] + v2[i] * u2[j] + v3[i] * u3[j];
+}
+
+// ---- hypotheses -------------------------------------------------------------------------------------------------------
+constexpr int HYP_THREADS = 256;
+
+__device__ __forceinline__ int cdf_search(const float* cdf, int n, float target) {
+  // first i with cdf[i] > target
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] > target) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// grid (groups of hypotheses, IM, B).  smem: X[3][n_s] Y[3][n_s] cdf[n_s]
+__global__ void __launch_bounds__(HYP_THREADS)
+ransac_hyp_kernel(const float* __restrict__ xyw, const int* __restrict__ inner_idx, int IM, int IR, int n_s,
+                  int hyp_per_block, float th_soft, unsigned long long seed, float* __restrict__ scores,
+                  float* __restrict__ Rt, int* __restrict__ status) {
+  extern __shared__ float sm[];
+  float* X = sm;                 // [3][n_s]
+  float* Y = sm + 3 * n_s;       // [3][n_s]
+  float* cdf = sm + 6 * n_s;     // [n_s] inclusive prefix sums of the weights
+  __shared__ float warp_tot[HYP_THREADS / 32];
+  const int s_in = blockIdx.y, b = blockIdx.z, s = b * IM + s_in;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* src = xyw + (long long)s * 8 * n_s;
+  for (int i = tid; i < 6 * n_s; i += HYP_THREADS) sm[i] = src[i];
+  // block-wide inclusive scan of the weights (n_s is a multiple of HYP_THREADS)
+  const int per = n_s / HYP_THREADS;
+  float run = 0.f;
+  for (int j = 0; j < per; ++j) { run += src[6 * n_s + tid * per + j]; cdf[tid * per + j] = run; }
+  float inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  float base = inc - run;
+  for (int w = 0; w < warp; ++w) base += warp_tot[w];
+  for (int j = 0; j < per; ++j) cdf[tid * per + j] += base;
+  __syncthreads();
+  const float W = cdf[n_s - 1];
+  const float beta = 5.0f / th_soft;
+  const Philox rng(seed ^ 0x9E3779B97F4A7C15ull);
+
+  const int h0 = blockIdx.x * hyp_per_block;
+  for (int hh = warp; hh < hyp_per_block; hh += HYP_THREADS / 32) {
+    const int h = h0 + hh;
+    if (h >= IR) break;
+    const long long gh = (long long)s * IR + h;
+    int id[3];
+    if (inner_idx) {
+      id[0] = inner_idx[gh * 3]; id[1] = inner_idx[gh * 3 + 1]; id[2] = inner_idx[gh * 3 + 2];
+    } else {
+      // successive sampling without replacement (== the exponential race in distribution)
+      const uint4 r = rng((uint32_t)h, (uint32_t)s_in, (uint32_t)b, 0x3c6ef372u);
+      const float u[3] = {u01_from_bits(r.x), u01_from_bits(r.y), u01_from_bits(r.z)};
+      float removed = 0.f;
+      for (int k = 0; k < 3; ++k) {
+        float target = u[k] * (W - removed);
+        // skip the mass of already drawn entries, in ascending index order
+        int a = (k > 0) ? id[0] : -1, c = (k > 1) ? id[1] : -1;
+        if (k > 1 && c < a) { const int t2 = a; a = c; c = t2; }
+        if (a >= 0) { const float ex = cdf[a] - ((a > 0) ? cdf[a - 1] : 0.f); if (target >= cdf[a] - ex) target += ex; }
+        if (c >= 0) { const float ex = cdf[c] - ((c > 0) ? cdf[c - 1] : 0.f); if (target >= cdf[c] - ex) target += ex; }
+        int pick = cdf_search(cdf, n_s, fminf(target, W * 0.99999994f));
+        // rounding may land on a removed entry: advance to the next free one
+        for (int guard = 0; guard < 3; ++guard)
+          if ((k > 0 && pick == id[0]) || (k > 1 && pick == id[1])) pick = (pick + 1) % n_s;
+        id[k] = pick;
+        removed += cdf[pick] - ((pick > 0) ? cdf[pick - 1] : 0.f);
+      }
+    }
+    // Kabsch on the 3 sampled correspondences (unweighted branch, solvers.py:32-39), replicated on all lanes
+    double xm[3] = {0, 0, 0}, ym[3] = {0, 0, 0};
+    float xk[3][3], yk[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        xk[k][c] = X[c * n_s + id[k]]; yk[k][c] = Y[c * n_s + id[k]];
+        xm[c] += xk[k][c]; ym[c] += yk[k][c];
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { xm[c] /= 3.0; ym[c] /= 3.0; }
+    double H[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) H[i * 3 + j] += ((double)xk[k][i] - xm[i]) * ((double)yk[k][j] - ym[j]);
+    double Rd[9];
+    kabsch_rotation(H, Rd);
+    float R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = (float)(ym[i] - (Rd[i * 3] * xm[0] + Rd[i * 3 + 1] * xm[1] + Rd[i * 3 + 2] * xm[2]));
+    // soft inlier count over the whole set (training_utils.py:55-61)
+    float sc = 0.f;
+    for (int i = lane; i < n_s; i += 32) {
+      const float x0 = X[i], x1 = X[n_s + i], x2 = X[2 * n_s + i];
+      const float r0 = R[0] * x0 + R[1] * x1 + R[2] * x2 + t[0] - Y[i];
+      const float r1 = R[3] * x0 + R[4] * x1 + R[5] * x2 + t[1] - Y[n_s + i];
+      const float r2 = R[6] * x0 + R[7] * x1 + R[8] * x2 + t[2] - Y[2 * n_s + i];
+      const float dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2 + 1e-6f);
+      sc += 1.0f / (1.0f + __expf(-beta * (th_soft - dist)));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    if (lane == 0) {
+      scores[gh] = sc;
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { Rt[gh * 12 + i] = R[i]; bad |= !isfinite(R[i]); }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { Rt[gh * 12 + 9 + i] = t[i]; bad |= !isfinite(t[i]); }
+      if (bad) atomicOr(status, 4);
+    }
+  }
+}
+
+// ---- finalize: argmax + refinement + final score -------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;
+
+__device__ __forceinline__ void block_reduce_sum(double* vals, int nvals, double* scratch /*[nvals][FIN_THREADS/32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < nvals; ++k) {
+    double v = vals[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) scratch[k * (FIN_THREADS / 32) + warp] = v;
+  }
+  __syncthreads();
+  for (int k = 0; k < nvals; ++k) {
+    double v = 0;
+    for (int w = 0; w < FIN_THREADS / 32; ++w) v += scratch[k * (FIN_THREADS / 32) + w];
+    vals[k] = v;
+  }
+  __syncthreads();
+}
+
+// out: pose [B,13] = R (9, row-major) | t (3) | inliers (1);  best_set [B];  inl_mask [B, n_s] (hard inliers @ final pose)
+__global__ void __launch_bounds__(FIN_THREADS)
+ransac_finalize_kernel(const float* __restrict__ xyw, const float* __restrict__ scores, const float* __restrict__ Rt,
+                       int IM, int IR, int n_s, int n_corr, int n_ref, float th_in, const int* __restrict__ status,
+                       float* __restrict__ pose, int* __restrict__ best_set, float* __restrict__ inl_mask,
+                       int* __restrict__ best_hyp) {
+  extern __shared__ float sm[];
+  float* X = sm;
+  float* Y = sm + 3 * n_s;
+  __shared__ float red_v[FIN_THREADS];
+  __shared__ int red_i[FIN_THREADS];
+  __shared__ double scratch[12 * (FIN_THREADS / 32)];
+  __shared__ float Rs[9], ts[3];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int total = IM * IR;
+  // argmax (first maximal index, like torch.argmax)
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int i = tid; i < total; i += FIN_THREADS) {
+    const float v = scores[(long long)b * total + i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  red_v[tid] = bv; red_i[tid] = bi;
+  __syncthreads();
+  for (int k = FIN_THREADS / 2; k; k >>= 1) {
+    if (tid < k) {
+      const float v = red_v[tid + k]; const int i = red_i[tid + k];
+      if (v > red_v[tid] || (v == red_v[tid] && i < red_i[tid])) { red_v[tid] = v; red_i[tid] = i; }
+    }
+    __syncthreads();
+  }
+  int best = red_i[0];
+  if (best < 0 || best >= total) best = 0;       // all-NaN scores
+  const int sset = b * IM + best / IR;
+  const float* src = xyw + (long long)sset * 8 * n_s;
+  for (int i = tid; i < 6 * n_s; i += FIN_THREADS) sm[i] = src[i];
+  if (tid < 9) Rs[tid] = Rt[((long long)b * total + best) * 12 + tid];
+  if (tid < 3) ts[tid] = Rt[((long long)b * total + best) * 12 + 9 + tid];
+  __syncthreads();
+
+  auto resid = [&](int i) {
+    const float x0 = X[i], x1 = X[n_s + i], x2 = X[2 * n_s + i];
+    const float r0 = Rs[0] * x0 + Rs[1] * x1 + Rs[2] * x2 + ts[0] - Y[i];
+    const float r1 = Rs[3] * x0 + Rs[4] * x1 + Rs[5] * x2 + ts[1] - Y[n_s + i];
+    const float r2 = Rs[6] * x0 + Rs[7] * x1 + Rs[8] * x2 + ts[2] - Y[2 * n_s + i];
+    return sqrtf(r0 * r0 + r1 * r1 + r2 * r2 + 1e-6f);
+  };
+
+  double prev = (double)n_corr;
+  for (int it = 0; it < n_ref; ++it) {
+    // hard inliers at the current pose (training_utils.py:71-75) and their moments
+    double m[7] = {0, 0, 0, 0, 0, 0, 0};          // count, sum x (3), sum y (3)
+    for (int i = tid; i < n_s; i += FIN_THREADS) {
+      if (th_in - resid(i) >= 0.f) {
+        m[0] += 1.0;
+        m[1] += X[i]; m[2] += X[n_s + i]; m[3] += X[2 * n_s + i];
+        m[4] += Y[i]; m[5] += Y[n_s + i]; m[6] += Y[2 * n_s + i];
+      }
+    }
+    block_reduce_sum(m, 7, scratch);
+    const double cnt = m[0];
+    if (!(cnt >= (double)n_corr && cnt > prev)) break;     // uniform across the block
+    prev = cnt;
+    const double wn = 1.0 / (cnt + 1e-16);                 // solvers.py:14-15 with a {0,1} mask
+    const double xm[3] = {m[1] * wn, m[2] * wn, m[3] * wn}, ym[3] = {m[4] * wn, m[5] * wn, m[6] * wn};
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n_s; i += FIN_THREADS) {
+      if (th_in - resid(i) >= 0.f) {
+        const double a[3] = {X[i] - xm[0], X[n_s + i] - xm[1], X[2 * n_s + i] - xm[2]};
+        const double c[3] = {Y[i] - ym[0], Y[n_s + i] - ym[1], Y[2 * n_s + i] - ym[2]};
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) H[p * 3 + q] += a[p] * c[q];
+      }
+    }
+    block_reduce_sum(H, 9, scratch);
+    if (tid == 0) {
+      double Rd[9];
+      kabsch_rotation(H, Rd);
+      for (int i = 0; i < 9; ++i) Rs[i] = (float)Rd[i];
+      for (int i = 0; i < 3; ++i) ts[i] = (float)(ym[i] - (Rd[i * 3] * xm[0] + Rd[i * 3 + 1] * xm[1] + Rd[i * 3 + 2] * xm[2]));
+    }
+    __syncthreads();
+  }
+  // final soft count at TH_INLIER (probabilisticProcrustes.py:303) + hard mask for the inlier list (:308)
+  const float beta = 5.0f / th_in;
+  double acc[1] = {0.0};
+  for (int i = tid; i < n_s; i += FIN_THREADS) {
+    const float d = resid(i);
+    acc[0] += 1.0f / (1.0f + __expf(-beta * (th_in - d)));
+    if (inl_mask) inl_mask[(long long)b * n_s + i] = (th_in - d >= 0.f) ? 1.0f : 0.0f;
+  }
+  block_reduce_sum(acc, 1, scratch);
+  if (tid == 0) {
+    const bool invalid = (*status & (1 | 4)) != 0;       // batch-level zero fallback (:261-262,329-342)
+    float* o = pose + (long long)b * 13;
+    for (int i = 0; i < 9; ++i) o[i] = invalid ? 0.f : Rs[i];
+    for (int i = 0; i < 3; ++i) o[9 + i] = invalid ? 0.f : ts[i];
+    o[12] = invalid ? 0.f : (float)acc[0];
+    best_set[b] = sset;
+    if (best_hyp) best_hyp[b] = best;
+  }
+}
+
+int ransac_solve(const float* final_scores, const float* kps0, const float* d0, const float* kps1, const float* d1,
+                 const float* K0, const float* K1, int B, int N, const RansacParams& rp, const int* outer_idx,
+                 const int* inner_idx, float* xyw, float* hyp_scores, float* hyp_Rt, int* status, float* pose,
+                 int* best_set, float* inl_mask, int* best_hyp, cudaStream_t st) {
+  const int IM = rp.it_matches, IR = rp.it_ransac, n_s = rp.n_sample;
+  if (rp.n_corr != 3) { set_last_error("NUM_CORR_3D_3D must be 3 (got %d)", rp.n_corr); return MK_ERR_UNSUPPORTED; }
+  if (n_s % HYP_THREADS) { set_last_error("NUM_SAMPLED_MATCHES must be a multiple of %d", HYP_THREADS); return MK_ERR_UNSUPPORTED; }
+  ransac_gather_kernel<<<B * IM, 256, 0, st>>>(outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, IM, n_s, xyw);
+  MK_CUDA_CHECK(cudaGetLastError());
+  const int hyp_per_block = 8;
+  const size_t smem_h = (size_t)7 * n_s * 4, smem_f = (size_t)6 * n_s * 4;
+  static bool attr = false;
+  if (!attr) {
+    MK_CUDA_CHECK(cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(ransac_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  if (smem_h > 200 * 1024) { set_last_error("NUM_SAMPLED_MATCHES too large for shared memory"); return MK_ERR_UNSUPPORTED; }
+  ransac_hyp_kernel<<<dim3(ceil_div(IR, hyp_per_block), IM, B), HYP_THREADS, smem_h, st>>>(
+      xyw, inner_idx, IM, IR, n_s, hyp_per_block, rp.th_soft, rp.seed, hyp_scores, hyp_Rt, status);
+  MK_CUDA_CHECK(cudaGetLastError());
+  ransac_finalize_kernel<<<B, FIN_THREADS, smem_f, st>>>(xyw, hyp_scores, hyp_Rt, IM, IR, n_s, rp.n_corr, rp.n_refine,
+                                                          rp.th_inlier, status, pose, best_set, inl_mask, best_hyp);
+  MK_CUDA_CHECK(cudaGetLastError());
+  return MK_OK;
+}
+
+}  // namespace mk

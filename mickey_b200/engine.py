@@ -1,0 +1,320 @@
+"""Device-side pipeline driver: packs a reference-named state dict into the layouts the CUDA kernels
+consume, owns the workspace, and calls the C ABI (include/mickey_b200.h) on the current CUDA stream.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic of the hot path happens inside
+libmickey_b200.so.  The only torch arithmetic in this file is weight preparation at load time:
+fp16 casts, BatchNorm folding into the conv weights, stacking the four heads, the bicubic resize of
+the position embedding (same torch call as the reference, dinov2.py:165-189) and the sine table.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .config import VARIANTS, backbone_variant
+from .weights import BACKBONE, DUSTBIN, EXTRACTOR
+
+HEAD_ORDER = ("depth_head", "det_offset", "det_head", "dsc_head")     # group order inside the kernels
+KPAD = 640
+PATCH = 14
+
+
+def make_mk_config(cfg) -> _lib.MkConfig:
+    variant = backbone_variant(cfg)
+    D, depth, heads = VARIANTS[variant]
+    m, p = cfg["MICKEY"], cfg["PROCRUSTES"]
+    if cfg["FEATURE_MATCHER"]["TYPE"] != "DualSoftmax":
+        # the reference's Sinkhorn branch is unreachable (feature_matcher.py:50 vs :125)
+        raise NotImplementedError("only FEATURE_MATCHER.TYPE == 'DualSoftmax' is supported")
+    c = _lib.MkConfig()
+    c.embed_dim, c.depth, c.heads = D, depth, heads
+    c.down_factor = int(m["DINOV2"]["DOWN_FACTOR"])
+    for i, v in enumerate(m["KP_HEADS"]["BLOCKS_DIM"]):
+        c.block_dims[i] = int(v)
+    c.desc_dim = int(m["DSC_HEAD"]["LAST_DIM"])
+    c.use_softmax = int(bool(m["KP_HEADS"]["USE_SOFTMAX"]))
+    c.depth_sigmoid = int(bool(m["KP_HEADS"]["USE_DEPTHSIGMOID"]))
+    c.max_depth = float(m["KP_HEADS"]["MAX_DEPTH"])
+    c.kp_pos_enc = int(bool(m["KP_HEADS"]["POS_ENCODING"]))
+    c.dsc_pos_enc = int(bool(m["DSC_HEAD"]["POS_ENCODING"]))
+    c.norm_dsc = int(bool(m["DSC_HEAD"]["NORM_DSC"]))
+    c.temperature = float(cfg["FEATURE_MATCHER"]["DUAL_SOFTMAX"]["TEMPERATURE"])
+    c.use_dustbin = int(bool(cfg["FEATURE_MATCHER"]["DUAL_SOFTMAX"]["USE_DUSTBIN"]))
+    c.it_matches, c.it_ransac = int(p["IT_MATCHES"]), int(p["IT_RANSAC"])
+    c.num_sampled, c.num_corr, c.num_refine = int(p["NUM_SAMPLED_MATCHES"]), int(p["NUM_CORR_3D_3D"]), int(p["NUM_REFINEMENTS"])
+    c.th_inlier, c.th_soft_inlier = float(p["TH_INLIER"]), float(p["TH_SOFT_INLIER"])
+    if c.down_factor != PATCH:
+        raise NotImplementedError("DOWN_FACTOR must be 14 (DINOv2 patch size)")
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------
+# weight packing
+# ---------------------------------------------------------------------------------------------------------
+def _fold_conv3x3(w: torch.Tensor, bn: Optional[Dict[str, torch.Tensor]]):
+    """[cout, cin, 3, 3] (+ eval BatchNorm) -> ([cout, 9*cin] with column = (ky*3+kx)*cin + ci, shift[cout])."""
+    cout, cin = w.shape[:2]
+    w = w.float()
+    if bn is not None:
+        scale = bn["weight"].float() / torch.sqrt(bn["running_var"].float() + 1e-5)
+        shift = bn["bias"].float() - bn["running_mean"].float() * scale
+    else:
+        scale = torch.ones(cout, device=w.device)
+        shift = torch.zeros(cout, device=w.device)
+    wp = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    return wp, shift
+
+
+def pack_weights(sd: Dict[str, torch.Tensor], cfg, device) -> Dict[str, torch.Tensor]:
+    """state dict with reference names (fp32 or fp16) -> {packed name: device tensor}."""
+    variant = backbone_variant(cfg)
+    D, depth, _ = VARIANTS[variant]
+    use_bn = bool(cfg["MICKEY"]["KP_HEADS"]["BN"])
+    out: Dict[str, torch.Tensor] = {}
+
+    def g(name):
+        return sd[name].detach().to(device)
+
+    def h16(t):
+        return t.to(torch.float16).contiguous()
+
+    def f32(t):
+        return t.to(torch.float32).contiguous()
+
+    b = BACKBONE
+    pw = g(b + "patch_embed.proj.weight").float().reshape(D, 3 * PATCH * PATCH)
+    out["patch.w"] = h16(F.pad(pw, (0, KPAD - pw.shape[1])))
+    for i in range(depth):
+        p, q = f"{b}blocks.{i}.", f"blk{i}."
+        out[q + "ln1.w"], out[q + "ln1.b"] = f32(g(p + "norm1.weight")), f32(g(p + "norm1.bias"))
+        out[q + "ln2.w"], out[q + "ln2.b"] = f32(g(p + "norm2.weight")), f32(g(p + "norm2.bias"))
+        out[q + "qkv.w"], out[q + "qkv.b"] = h16(g(p + "attn.qkv.weight")), f32(g(p + "attn.qkv.bias"))
+        out[q + "proj.w"], out[q + "proj.b"] = h16(g(p + "attn.proj.weight")), f32(g(p + "attn.proj.bias"))
+        out[q + "fc1.w"], out[q + "fc1.b"] = h16(g(p + "mlp.fc1.weight")), f32(g(p + "mlp.fc1.bias"))
+        out[q + "fc2.w"], out[q + "fc2.b"] = h16(g(p + "mlp.fc2.weight")), f32(g(p + "mlp.fc2.bias"))
+        out[q + "ls1"], out[q + "ls2"] = f32(g(p + "ls1.gamma")), f32(g(p + "ls2.gamma"))
+    out["norm.w"], out["norm.b"] = f32(g(b + "norm.weight")), f32(g(b + "norm.bias"))
+
+    def bn_of(prefix):
+        if not use_bn:
+            return None
+        return {k: g(prefix + k) for k in ("weight", "bias", "running_mean", "running_var")}
+
+    def block(head, r):
+        rp = f"{EXTRACTOR}{head}.resblock{r}."
+        w1, s1 = _fold_conv3x3(g(rp + "conv1.weight"), bn_of(rp + "bn1."))
+        w2, s2 = _fold_conv3x3(g(rp + "conv2.weight"), bn_of(rp + "bn2."))
+        sc = sd.get(rp + "shortcut.0.weight")
+        sc = None if sc is None else sc.detach().to(device).float().reshape(sc.shape[0], sc.shape[1])
+        return w1, s1, w2, s2, sc
+
+    for r in (1, 2, 3):
+        parts = [block(hd, r) for hd in HEAD_ORDER]
+        assert all(p[4] is not None for p in parts), "resblocks 1-3 change width and must have a shortcut conv"
+        out[f"rb{r}.c1.w"], out[f"rb{r}.c1.b"] = h16(torch.cat([p[0] for p in parts])), f32(torch.cat([p[1] for p in parts]))
+        out[f"rb{r}.c2.w"], out[f"rb{r}.c2.b"] = h16(torch.cat([p[2] for p in parts])), f32(torch.cat([p[3] for p in parts]))
+        out[f"rb{r}.sc.w"] = h16(torch.cat([p[4] for p in parts]))
+    kparts = [block(hd, 4) for hd in HEAD_ORDER[:3]]
+    out["rb4k.c1.w"], out["rb4k.c1.b"] = h16(torch.cat([p[0] for p in kparts])), f32(torch.cat([p[1] for p in kparts]))
+    out["rb4k.c2.w"], out["rb4k.c2.b"] = h16(torch.cat([p[2] for p in kparts])), f32(torch.cat([p[3] for p in kparts]))
+    out["rb4k.sc.w"] = h16(torch.cat([p[4] for p in kparts]))
+    d = block("dsc_head", 4)
+    if d[4] is not None:
+        raise NotImplementedError("descriptor head with LAST_DIM != 128 (shortcut conv in resblock4) is not supported")
+    out["rb4d.c1.w"], out["rb4d.c1.b"], out["rb4d.c2.w"], out["rb4d.c2.b"] = h16(d[0]), f32(d[1]), h16(d[2]), f32(d[3])
+
+    for l in range(3):
+        def lw(name):
+            return [g(f"{EXTRACTOR}{hd}.att_layer.layers.{l}.{name}").float() for hd in HEAD_ORDER]
+        qkv = [torch.cat([q_, k_, v_]) for q_, k_, v_ in zip(lw("q_proj.weight"), lw("k_proj.weight"), lw("v_proj.weight"))]
+        out[f"att{l}.qkv.w"] = h16(torch.cat(qkv))
+        out[f"att{l}.merge.w"] = h16(torch.cat(lw("merge.weight")))
+        out[f"att{l}.mlp0.w"] = h16(torch.cat(lw("mlp.0.weight")))
+        out[f"att{l}.mlp2.w"] = h16(torch.cat(lw("mlp.2.weight")))
+        out[f"att{l}.n1.w"], out[f"att{l}.n1.b"] = f32(torch.cat(lw("norm1.weight"))), f32(torch.cat(lw("norm1.bias")))
+        out[f"att{l}.n2.w"], out[f"att{l}.n2.b"] = f32(torch.cat(lw("norm2.weight"))), f32(torch.cat(lw("norm2.bias")))
+
+    out["out.depth.w"] = f32(g(EXTRACTOR + "depth_head.depth.weight").reshape(-1))
+    out["out.xy.w"] = f32(g(EXTRACTOR + "det_offset.xy_offset.weight").reshape(-1))
+    out["out.score.w"] = f32(g(EXTRACTOR + "det_head.score.weight").reshape(-1))
+    if DUSTBIN in sd:
+        out["dustbin"] = f32(g(DUSTBIN).reshape(1))
+    return out
+
+
+def interpolate_pos_embed(pos_embed: torch.Tensor, gh: int, gw: int) -> torch.Tensor:
+    """Resize the square position-embedding grid to (gh, gw) exactly as the reference does
+    (dinov2.py:165-189: bicubic, scale_factor with the +0.1 trick).  Returns [1 + gh*gw, D] fp32."""
+    pe = pos_embed.float()
+    n = pe.shape[1] - 1
+    gs = int(math.sqrt(n))
+    dim = pe.shape[-1]
+    if gh * gw == n and gh == gw:
+        return pe[0]
+    grid = pe[:, 1:].reshape(1, gs, gs, dim).permute(0, 3, 1, 2)
+    grid = F.interpolate(grid, scale_factor=((gh + 0.1) / gs, (gw + 0.1) / gs), mode="bicubic")
+    assert grid.shape[-2:] == (gh, gw)
+    return torch.cat([pe[0, :1], grid.permute(0, 2, 3, 1).reshape(gh * gw, dim)], dim=0)
+
+
+def sine_table_padded(gh: int, gw: int, d_model: int = 128) -> torch.Tensor:
+    """2-D sine position encoding (att_layers/transformer.py:25-36, positions start at 1) laid out on
+    the zero-padded token grid: [(gh+2)*(gw+2), d_model], zeros on the pad ring."""
+    y = torch.arange(1, gh + 1, dtype=torch.float32).view(gh, 1).expand(gh, gw)
+    x = torch.arange(1, gw + 1, dtype=torch.float32).view(1, gw).expand(gh, gw)
+    div = torch.exp(torch.arange(0, d_model // 2, 2).float() * (-math.log(10000.0) / (d_model // 2)))
+    pe = torch.zeros(gh, gw, d_model)
+    pe[..., 0::4] = torch.sin(x[..., None] * div)
+    pe[..., 1::4] = torch.cos(x[..., None] * div)
+    pe[..., 2::4] = torch.sin(y[..., None] * div)
+    pe[..., 3::4] = torch.cos(y[..., None] * div)
+    out = torch.zeros(gh + 2, gw + 2, d_model)
+    out[1:-1, 1:-1] = pe
+    return out.reshape(-1, d_model).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class Engine:
+    """One C handle + packed weights + workspace for a fixed (cfg, device)."""
+
+    def __init__(self, cfg, device):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MickeyB200Error("mickey_b200 runs on a CUDA device only (sm_100a); there is no CPU path")
+        self.mkcfg = make_mk_config(cfg)
+        h = C.c_void_p()
+        _lib.check(self.lib.mk_create(self.device.index or 0, C.byref(self.mkcfg), C.byref(h)), "mk_create")
+        self.h = h
+        self.packed: Dict[str, torch.Tensor] = {}
+        self._raw_pos = None
+        self.geo = None
+        self.ws = None
+        self.ws_pairs = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.mk_destroy(self.h)
+        except Exception:
+            pass
+
+    # -- weights ---------------------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        with torch.no_grad():
+            self.packed = pack_weights(sd, self.cfg, self.device)
+            self._raw_pos = (sd[BACKBONE + "pos_embed"].detach().to(self.device).float(),
+                             sd[BACKBONE + "cls_token"].detach().to(self.device).float(),
+                             sd[BACKBONE + "patch_embed.proj.bias"].detach().to(self.device).float())
+        for name, t in self.packed.items():
+            self._register(name, t)
+        self.geo = None
+
+    def _register(self, name, t):
+        assert t.is_contiguous() and t.device == self.device
+        dt = {torch.float32: 0, torch.float16: 1}[t.dtype]
+        _lib.check(self.lib.mk_set_tensor(self.h, name.encode(), _lib.ptr(t), dt, t.numel()), f"mk_set_tensor({name})")
+
+    def prepare(self, n_pairs: int, H: int, W: int):
+        """Size-dependent tables + workspace for images cropped to (H, W) (multiples of 14)."""
+        assert self.packed, "load_state_dict first"
+        if self.geo != (H, W):
+            gh, gw = H // PATCH, W // PATCH
+            with torch.no_grad():
+                pos, cls, pbias = self._raw_pos
+                full = interpolate_pos_embed(pos, gh, gw)
+                self.packed["patch.posb"] = (full[1:] + pbias[None]).contiguous()
+                self.packed["patch.clspos"] = (cls.reshape(-1) + full[0]).contiguous()
+                self.packed["head.pe"] = sine_table_padded(gh, gw).to(self.device)
+            for n in ("patch.posb", "patch.clspos", "head.pe"):
+                self._register(n, self.packed[n])
+            _lib.check(self.lib.mk_finalize(self.h, H, W), "mk_finalize")
+            self.geo = (H, W)
+            self.ws = None
+        if self.ws is None or self.ws_pairs < n_pairs:
+            nbytes = self.lib.mk_workspace_bytes(self.h, n_pairs, H, W)
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.ws_pairs = n_pairs
+        return self.ws
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mk_launch_count(self.h))
+
+    def _ws_for(self, n_pairs, H, W):
+        # the workspace layout depends on n_pairs: carve exactly for this call's batch
+        self.prepare(n_pairs, H, W)
+        if self.ws_pairs != n_pairs:
+            nbytes = self.lib.mk_workspace_bytes(self.h, n_pairs, H, W)
+            if self.ws.numel() < nbytes:
+                self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.ws_pairs = n_pairs
+        return self.ws
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # -- stages ------------------------------------------------------------------------------------------------
+    def crop(self, images: torch.Tensor) -> torch.Tensor:
+        H, W = images.shape[-2:]
+        Hc, Wc = PATCH * (H // PATCH), PATCH * (W // PATCH)
+        if (Hc, Wc) != (H, W):
+            images = images[..., :Hc, :Wc]
+        return images.contiguous()
+
+    def extract(self, images: torch.Tensor):
+        """images fp32 [2B, 3, H, W] (image0 batch then image1 batch) -> kps, depth, scr, dsc."""
+        images = self.crop(images.float())
+        n_img, _, H, W = images.shape
+        assert n_img % 2 == 0
+        B, N = n_img // 2, (H // PATCH) * (W // PATCH)
+        ws = self._ws_for(B, H, W)
+        dev = self.device
+        kps = torch.empty(n_img, 2, N, device=dev)
+        depth = torch.empty(n_img, 1, N, device=dev)
+        scr = torch.empty(n_img, 1, N, device=dev)
+        dsc = torch.empty(n_img, self.mkcfg.desc_dim, N, device=dev)
+        _lib.check(self.lib.mk_extract(self.h, _lib.ptr(images), B, H, W, _lib.ptr(kps), _lib.ptr(depth), _lib.ptr(scr),
+                                       _lib.ptr(dsc), _lib.ptr(ws), ws.numel(), self._stream()), "mk_extract")
+        return kps, depth, scr, dsc
+
+    def match(self, B: int, N: int):
+        dev = self.device
+        scores = torch.empty(B, N, N, device=dev)
+        kp_scores = torch.empty(B, N, N, device=dev)
+        final = torch.empty(B, N, N, device=dev)
+        _lib.check(self.lib.mk_match(self.h, B, _lib.ptr(scores), _lib.ptr(kp_scores), _lib.ptr(final),
+                                     _lib.ptr(self.ws), self.ws.numel(), self._stream()), "mk_match")
+        return scores, kp_scores, final
+
+    def solve(self, final_scores, kps, depth, K0, K1, seed: int, outer_idx=None, inner_idx=None, want_extras=False):
+        """kps [2B,2,N], depth [2B,1,N] as produced by extract (image0 rows first)."""
+        B, N, _ = final_scores.shape
+        dev = self.device
+        c = self.mkcfg
+        pose = torch.empty(B, 13, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        best_set = torch.empty(B, dtype=torch.int32, device=dev) if want_extras else None
+        mask = torch.empty(B, c.num_sampled, device=dev) if want_extras else None
+        sampled = torch.empty(B * c.it_matches, c.num_sampled, dtype=torch.int32, device=dev) if want_extras else None
+        hyp = torch.empty(B, c.it_matches * c.it_ransac, device=dev) if want_extras else None
+        if outer_idx is not None:
+            outer_idx = outer_idx.to(dev, torch.int32).contiguous()
+        if inner_idx is not None:
+            inner_idx = inner_idx.to(dev, torch.int32).contiguous()
+        K0 = K0.to(dev, torch.float32).contiguous()
+        K1 = K1.to(dev, torch.float32).contiguous()
+        _lib.check(self.lib.mk_solve_pose(
+            self.h, _lib.ptr(final_scores), _lib.ptr(kps), _lib.ptr(depth), _lib.ptr(K0), _lib.ptr(K1), B, N,
+            C.c_ulonglong(seed & (2 ** 64 - 1)), _lib.ptr(outer_idx), _lib.ptr(inner_idx), _lib.ptr(pose),
+            _lib.ptr(best_set), _lib.ptr(mask), _lib.ptr(sampled), _lib.ptr(hyp), _lib.ptr(status),
+            _lib.ptr(self.ws), self.ws.numel(), self._stream()), "mk_solve_pose")
+        return {"pose": pose, "status": status, "best_set": best_set, "inlier_mask": mask, "sampled_idx": sampled,
+                "hyp_scores": hyp}
