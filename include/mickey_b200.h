@@ -98,6 +98,10 @@ int mk_forward(mk_handle* h, const float* images_dev, const float* K0_dev, const
 
 /* Number of kernel launches issued by this library since the handle was created (for bench.py). */
 long long mk_launch_count(mk_handle* h);
+/* Per-kernel-class device timing: while enabled every launch issued by the stages is bracketed by CUDA
+ * events on the launch stream; mk_profile_read synchronises and writes "<class> <scopes> <total ms>" lines. */
+int mk_profile_enable(mk_handle* h, int enable);
+int mk_profile_read(mk_handle* h, char* buf, int buf_bytes);
 
 /* ---- operator-level entry points (unit tests of single kernels; not needed by an integrator) ---- */
 typedef struct mk_gemm_args {

@@ -74,6 +74,8 @@ EXPORTS = {
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
                              C.c_void_p]),
     "mk_launch_count": (C.c_longlong, [C.c_void_p]),
+    "mk_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "mk_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "mk_op_gemm": (C.c_int, [C.POINTER(MkGemmArgs), C.c_void_p]),
     "mk_op_patch_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p]),

@@ -20,6 +20,10 @@ struct mk_handle {
   int geo_h = 0, geo_w = 0;
   bool finalized = false;
   long long launches = 0;
+  // optional per-kernel-class timing with CUDA events on the launch stream (mk_profile_*)
+  bool profiling = false;
+  struct ProfRec { std::string tag; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -144,12 +148,28 @@ void set_conv_taps(GemmParams& p, int cin, int w2, bool three) {
 
 #define MK_TRY(x) do { int rc_ = (x); if (rc_ != MK_OK) return rc_; } while (0)
 
-int gemm(mk_handle* h, int epi, const void* a, long long a_rows, long long a_cols, const void* b, long long b_rows,
-         long long b_cols, const GemmParams& p, cudaStream_t st) {
+struct ProfScope {
+  mk_handle* h; cudaStream_t st; int slot = -1;
+  ProfScope(mk_handle* h_, const char* tag, cudaStream_t st_) : h(h_), st(st_) {
+    if (!h->profiling) return;
+    mk_handle::ProfRec r;
+    r.tag = tag;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    h->prof.push_back(r);
+    slot = (int)h->prof.size() - 1;
+  }
+  ~ProfScope() { if (slot >= 0) cudaEventRecord(h->prof[slot].e1, st); }
+};
+
+int gemm(mk_handle* h, const char* tag, int epi, const void* a, long long a_rows, long long a_cols, const void* b,
+         long long b_rows, long long b_cols, const GemmParams& p, cudaStream_t st) {
   GemmOperand A{a, a_rows, a_cols, a_cols}, B{b, b_rows, b_cols, b_cols};
   h->launches++;
+  ProfScope ps(h, tag, st);
   return launch_gemm(epi, A, B, p, st);
 }
+#define MK_KERNEL(tag, call) do { ProfScope ps_(h, tag, st); h->launches++; MK_TRY(call); } while (0)
 
 // ---- stage 1 ----------------------------------------------------------------------------------------------
 int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, float* kps, float* depth, float* scr,
@@ -159,13 +179,13 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
   const int D = c.embed_dim;
   Lookup L{h};
   // -- tokens: patch embedding + cls + position embedding (dinov2.py:191-200)
-  MK_TRY(patch_gather(images, w.P, g.n_img, H, W, KPAD, w.X, L.f("patch.clspos", D), D, st)); h->launches++;
+  MK_KERNEL("vit.patch_gather", patch_gather(images, w.P, g.n_img, H, W, KPAD, w.X, L.f("patch.clspos", D), D, st));
   {
     GemmParams p = base_params(g.Mp, D, KPAD);
     p.aux = L.f("patch.posb", (long long)g.N * D); p.tok_per_img = g.N; p.out_f = w.X; p.out_f_ld = D;
     const __half* wt = L.hh("patch.w", (long long)D * KPAD);
     if (!L.ok) return MK_ERR_MISSING_TENSOR;
-    MK_TRY(gemm(h, EPI_PATCH, w.P, g.Mp, KPAD, wt, D, KPAD, p, st));
+    MK_TRY(gemm(h, "vit.patch_embed", EPI_PATCH, w.P, g.Mp, KPAD, wt, D, KPAD, p, st));
   }
   // -- transformer blocks (layers/block.py:105-106)
   for (int i = 0; i < c.depth; ++i) {
@@ -176,21 +196,21 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
     const float *bqkv = L.f(b + "qkv.b", 3 * D), *bproj = L.f(b + "proj.b", D), *bfc1 = L.f(b + "fc1.b", 4 * D), *bfc2 = L.f(b + "fc2.b", D);
     const float *ls1 = L.f(b + "ls1", D), *ls2 = L.f(b + "ls2", D);
     if (!L.ok) return MK_ERR_MISSING_TENSOR;
-    MK_TRY(layernorm(w.X, ln1w, ln1b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st)); h->launches++;
+    MK_KERNEL("vit.layernorm", layernorm(w.X, ln1w, ln1b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st));
     { GemmParams p = base_params(g.M, 3 * D, D); p.bias = bqkv; p.out_h = w.QKV; p.out_h_ld = 3 * D;
-      MK_TRY(gemm(h, EPI_STORE_H, w.XN, g.M, D, wqkv, 3 * D, D, p, st)); }
-    MK_TRY(attention(w.QKV, w.ATT, g.n_img, g.T, D, c.heads, st)); h->launches++;
+      MK_TRY(gemm(h, "vit.qkv", EPI_STORE_H, w.XN, g.M, D, wqkv, 3 * D, D, p, st)); }
+    MK_KERNEL("vit.attention", attention(w.QKV, w.ATT, g.n_img, g.T, D, c.heads, st));
     { GemmParams p = base_params(g.M, D, D); p.bias = bproj; p.gamma = ls1; p.out_f = w.X; p.out_f_ld = D;
-      MK_TRY(gemm(h, EPI_RESID_F, w.ATT, g.M, D, wproj, D, D, p, st)); }
-    MK_TRY(layernorm(w.X, ln2w, ln2b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st)); h->launches++;
+      MK_TRY(gemm(h, "vit.proj", EPI_RESID_F, w.ATT, g.M, D, wproj, D, D, p, st)); }
+    MK_KERNEL("vit.layernorm", layernorm(w.X, ln2w, ln2b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st));
     { GemmParams p = base_params(g.M, 4 * D, D); p.bias = bfc1; p.act = ACT_GELU; p.out_h = w.H1; p.out_h_ld = 4 * D;
-      MK_TRY(gemm(h, EPI_STORE_H, w.XN, g.M, D, wfc1, 4 * D, D, p, st)); }
+      MK_TRY(gemm(h, "vit.fc1", EPI_STORE_H, w.XN, g.M, D, wfc1, 4 * D, D, p, st)); }
     { GemmParams p = base_params(g.M, D, 4 * D); p.bias = bfc2; p.gamma = ls2; p.out_f = w.X; p.out_f_ld = D;
-      MK_TRY(gemm(h, EPI_RESID_F, w.H1, g.M, 4 * D, wfc2, D, 4 * D, p, st)); }
+      MK_TRY(gemm(h, "vit.fc2", EPI_RESID_F, w.H1, g.M, 4 * D, wfc2, D, 4 * D, p, st)); }
   }
   // -- final norm, drop cls, scatter into the zero-padded NHWC feature image (dinov2.py:230-233, mickey_extractor.py:49-51)
   MK_CUDA_CHECK(cudaMemsetAsync(w.F, 0, (size_t)g.R * D * sizeof(__half), st));
-  MK_TRY(layernorm(w.X, L.f("norm.w", D), L.f("norm.b", D), w.F, (int)g.M, D, 1e-6f, 1, g.gh, g.gw, st)); h->launches++;
+  MK_KERNEL("vit.layernorm", layernorm(w.X, L.f("norm.w", D), L.f("norm.b", D), w.F, (int)g.M, D, 1e-6f, 1, g.gh, g.gw, st));
   if (!L.ok) return MK_ERR_MISSING_TENSOR;
 
   // -- heads: three grouped residual blocks (extractor_utils.py:28-35; G = 4 heads side by side in channels)
@@ -212,13 +232,13 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
       GemmParams p = base_params(g.R, rb.cout, 64); set_conv_taps(p, rb.cin, g.w2, true);
       p.groups = G; p.a_col_group_off = rb.in_goff; p.b_row_group_off = rb.cout; p.bias = b1; p.bias_group_off = rb.cout;
       p.act = ACT_RELU; p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_h = rb.T; p.out_h_ld = (long long)G * rb.cout; p.out_h_group_off = rb.cout;
-      MK_TRY(gemm(h, EPI_CONV, rb.in, g.R, in_cols, wc1, (long long)G * rb.cout, 9LL * rb.cin, p, st));
+      MK_TRY(gemm(h, "head.conv3x3", EPI_CONV, rb.in, g.R, in_cols, wc1, (long long)G * rb.cout, 9LL * rb.cin, p, st));
     }
     {  // 1x1 shortcut
       GemmParams p = base_params(g.R, rb.cout, 64); set_conv_taps(p, rb.cin, g.w2, false);
       p.groups = G; p.a_col_group_off = rb.in_goff; p.b_row_group_off = rb.cout;
       p.out_h = rb.S; p.out_h_ld = (long long)G * rb.cout; p.out_h_group_off = rb.cout;
-      MK_TRY(gemm(h, EPI_CONV, rb.in, g.R, in_cols, wsc, (long long)G * rb.cout, rb.cin, p, st));
+      MK_TRY(gemm(h, "head.conv1x1", EPI_CONV, rb.in, g.R, in_cols, wsc, (long long)G * rb.cout, rb.cin, p, st));
     }
     {  // conv2 + bn2 + shortcut + relu (+ sine position encoding and fp32 copy after block 3)
       GemmParams p = base_params(g.R, rb.cout, 64); set_conv_taps(p, rb.cout, g.w2, true);
@@ -233,7 +253,7 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
         p.aux_group_mask = (c.kp_pos_enc ? 0x7 : 0) | (c.dsc_pos_enc ? 0x8 : 0);
         if (!L.ok) return MK_ERR_MISSING_TENSOR;
       }
-      MK_TRY(gemm(h, EPI_CONV, rb.T, g.R, (long long)G * rb.cout, wc2, (long long)G * rb.cout, 9LL * rb.cout, p, st));
+      MK_TRY(gemm(h, "head.conv3x3", EPI_CONV, rb.T, g.R, (long long)G * rb.cout, wc2, (long long)G * rb.cout, 9LL * rb.cout, p, st));
     }
   }
   // -- linear-attention transformer, 3 layers (att_layers/transformer_utils.py:40-66)
@@ -245,22 +265,22 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
     if (!L.ok) return MK_ERR_MISSING_TENSOR;
     { GemmParams p = base_params(g.R, 384, 128); p.groups = G; p.a_col_group_off = 256; p.b_row_group_off = 384;
       p.out_f = w.QKV32; p.out_f_ld = G * 384; p.out_f_group_off = 384;
-      MK_TRY(gemm(h, EPI_STORE_F, w.CAT, g.R, G * 256, wqkv, G * 384, 128, p, st)); }
-    MK_TRY(linattn_kv(w.QKV32, w.KV, g.n_img, G, g.h2, g.w2, st)); h->launches++;
-    MK_TRY(linattn_msg(w.QKV32, w.KV, w.MSG, g.n_img, G, g.h2, g.w2, 1e-6f, st)); h->launches++;
+      MK_TRY(gemm(h, "head.att.qkv", EPI_STORE_F, w.CAT, g.R, G * 256, wqkv, G * 384, 128, p, st)); }
+    MK_KERNEL("head.att.kv", linattn_kv(w.QKV32, w.KV, g.n_img, G, g.h2, g.w2, st));
+    MK_KERNEL("head.att.msg", linattn_msg(w.QKV32, w.KV, w.MSG, g.n_img, G, g.h2, g.w2, 1e-6f, st));
     { GemmParams p = base_params(g.R, 128, 128); p.groups = G; p.a_col_group_off = 128; p.b_row_group_off = 128;
       p.gamma = n1w; p.beta = n1b; p.ln_group_off = 128; p.eps = 1e-5f;
       p.out_h = w.CAT + 128; p.out_h_ld = G * 256; p.out_h_group_off = 256;
-      MK_TRY(gemm(h, EPI_LN, w.MSG, g.R, G * 128, wmerge, G * 128, 128, p, st)); }
+      MK_TRY(gemm(h, "head.att.merge_ln", EPI_LN, w.MSG, g.R, G * 128, wmerge, G * 128, 128, p, st)); }
     { GemmParams p = base_params(g.R, 256, 256); p.groups = G; p.a_col_group_off = 256; p.b_row_group_off = 256; p.act = ACT_RELU;
       p.out_h = w.HM; p.out_h_ld = G * 256; p.out_h_group_off = 256;
-      MK_TRY(gemm(h, EPI_STORE_H, w.CAT, g.R, G * 256, wm0, G * 256, 256, p, st)); }
+      MK_TRY(gemm(h, "head.att.mlp0", EPI_STORE_H, w.CAT, g.R, G * 256, wm0, G * 256, 256, p, st)); }
     { GemmParams p = base_params(g.R, 128, 256); p.groups = G; p.a_col_group_off = 256; p.b_row_group_off = 128;
       p.gamma = n2w; p.beta = n2b; p.ln_group_off = 128; p.eps = 1e-5f;
       p.out_f = w.X32; p.out_f_ld = G * 128; p.out_f_group_off = 128;
       p.out_h = w.CAT; p.out_h_ld = G * 256; p.out_h_group_off = 256;
       if (l == 2) { p.pad_h2 = g.h2; p.pad_w2 = g.w2; }       // zero the pad rows again before the next 3x3 conv
-      MK_TRY(gemm(h, EPI_LN, w.HM, g.R, G * 256, wm2, G * 128, 256, p, st)); }
+      MK_TRY(gemm(h, "head.att.mlp2_ln", EPI_LN, w.HM, g.R, G * 256, wm2, G * 128, 256, p, st)); }
   }
   // -- residual block 4: three keypoint heads (128 -> 64, with shortcut conv) and the descriptor head (128 -> desc_dim)
   {
@@ -271,15 +291,15 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
     { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, 128, g.w2, true);
       p.groups = 3; p.a_col_group_off = 256; p.b_row_group_off = co; p.bias = b1; p.bias_group_off = co; p.act = ACT_RELU;
       p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_h = w.T4k; p.out_h_ld = 3 * co; p.out_h_group_off = co;
-      MK_TRY(gemm(h, EPI_CONV, w.CAT, g.R, G * 256, wc1, 3 * co, 9 * 128, p, st)); }
+      MK_TRY(gemm(h, "head.conv3x3", EPI_CONV, w.CAT, g.R, G * 256, wc1, 3 * co, 9 * 128, p, st)); }
     { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, 128, g.w2, false);
       p.groups = 3; p.a_col_group_off = 256; p.b_row_group_off = co; p.out_h = w.S4k; p.out_h_ld = 3 * co; p.out_h_group_off = co;
-      MK_TRY(gemm(h, EPI_CONV, w.CAT, g.R, G * 256, wsc, 3 * co, 128, p, st)); }
+      MK_TRY(gemm(h, "head.conv1x1", EPI_CONV, w.CAT, g.R, G * 256, wsc, 3 * co, 128, p, st)); }
     { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, co, g.w2, true);
       p.groups = 3; p.a_col_group_off = co; p.b_row_group_off = co; p.bias = b2; p.bias_group_off = co; p.act = ACT_RELU;
       p.res_h = w.S4k; p.res_h_ld = 3 * co; p.res_h_group_off = co; p.pad_h2 = g.h2; p.pad_w2 = g.w2;
       p.out_f = w.Y4k; p.out_f_ld = 3 * co; p.out_f_group_off = co;
-      MK_TRY(gemm(h, EPI_CONV, w.T4k, g.R, 3 * co, wc2, 3 * co, 9 * co, p, st)); }
+      MK_TRY(gemm(h, "head.conv3x3", EPI_CONV, w.T4k, g.R, 3 * co, wc2, 3 * co, 9 * co, p, st)); }
   }
   {
     const int co = c.desc_dim;
@@ -289,19 +309,19 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
     if (!L.ok) return MK_ERR_MISSING_TENSOR;
     { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, 128, g.w2, true);
       p.a_col_base = 3 * 256; p.bias = b1; p.act = ACT_RELU; p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_h = w.T4d; p.out_h_ld = co;
-      MK_TRY(gemm(h, EPI_CONV, w.CAT, g.R, G * 256, wc1, co, 9 * 128, p, st)); }
+      MK_TRY(gemm(h, "head.conv3x3", EPI_CONV, w.CAT, g.R, G * 256, wc1, co, 9 * 128, p, st)); }
     { GemmParams p = base_params(g.R, co, 64); set_conv_taps(p, co, g.w2, true);
       p.bias = b2; p.act = ACT_NONE; p.res_h = w.CAT + 3 * 256; p.res_h_ld = G * 256;   // identity shortcut (in == out planes)
       p.pad_h2 = g.h2; p.pad_w2 = g.w2; p.out_f = w.Y4d; p.out_f_ld = co;
-      MK_TRY(gemm(h, EPI_CONV, w.T4d, g.R, co, wc2, co, 9 * co, p, st)); }
+      MK_TRY(gemm(h, "head.conv3x3", EPI_CONV, w.T4d, g.R, co, wc2, co, 9 * co, p, st)); }
   }
   // -- output layers and activations
-  MK_TRY(kp_head_out(w.Y4k, L.f("out.depth.w", bd[3]), L.f("out.xy.w", 2 * bd[3]), L.f("out.score.w", bd[3]), depth, kps,
-                     w.score_raw, scr, g.n_img, g.gh, g.gw, c.depth_sigmoid, c.max_depth, (float)c.down_factor, c.use_softmax, st));
-  h->launches += 2;
+  { ProfScope ps_(h, "head.kp_out", st); h->launches += 2;
+    MK_TRY(kp_head_out(w.Y4k, L.f("out.depth.w", bd[3]), L.f("out.xy.w", 2 * bd[3]), L.f("out.score.w", bd[3]), depth, kps,
+                       w.score_raw, scr, g.n_img, g.gh, g.gw, c.depth_sigmoid, c.max_depth, (float)c.down_factor, c.use_softmax, st)); }
   if (!L.ok) return MK_ERR_MISSING_TENSOR;
   if (bd[3] != 64) { set_last_error("KP_HEADS.BLOCKS_DIM[3] must be 64"); return MK_ERR_UNSUPPORTED; }
-  MK_TRY(desc_out(w.Y4d, dsc, w.DSCX, w.nrm2, g.n_img, g.gh, g.gw, c.norm_dsc, st)); h->launches++;
+  MK_KERNEL("head.desc_out", desc_out(w.Y4d, dsc, w.DSCX, w.nrm2, g.n_img, g.gh, g.gw, c.norm_dsc, st));
   MK_CUDA_CHECK(cudaMemcpyAsync(w.scr_copy, scr, (size_t)g.n_img * g.N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return MK_OK;
 }
@@ -318,7 +338,7 @@ int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores,
     return MK_ERR_UNSUPPORTED;
   }
   const float inv_t = 1.0f / c.temperature;
-  MK_TRY(matcher_prep(w.nrm2, dust, inv_t, w.shift, w.row_sum, w.col_sum, n_pairs, N, st)); h->launches++;
+  MK_KERNEL("match.prep", matcher_prep(w.nrm2, dust, inv_t, w.shift, w.row_sum, w.col_sum, n_pairs, N, st));
   const __half* A0 = w.DSCX;                                   // role-0 descriptors [n_pairs*N, 384]
   const __half* A1 = w.DSCX + (size_t)n_pairs * N * 384;       // role-1 descriptors
   const long long rows = (long long)n_pairs * N;
@@ -328,11 +348,11 @@ int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores,
     p.shift = w.shift; p.dustbin = dust;
     return p;
   };
-  { GemmParams p = mp(); p.row_sum = w.row_sum; MK_TRY(gemm(h, EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
-  { GemmParams p = mp(); p.row_sum = w.col_sum; MK_TRY(gemm(h, EPI_LSE, A1, rows, 384, A0, rows, 384, p, st)); }
+  { GemmParams p = mp(); p.row_sum = w.row_sum; MK_TRY(gemm(h, "match.lse", EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
+  { GemmParams p = mp(); p.row_sum = w.col_sum; MK_TRY(gemm(h, "match.lse", EPI_LSE, A1, rows, 384, A0, rows, 384, p, st)); }
   { GemmParams p = mp(); p.rs = w.row_sum; p.cs = w.col_sum; p.scr0 = w.scr_copy; p.scr1 = w.scr_copy + (size_t)n_pairs * N;
     p.scores = scores; p.kp_scores = kp_scores; p.final_scores = final_scores;
-    MK_TRY(gemm(h, EPI_DUAL, A0, rows, 384, A1, rows, 384, p, st)); }
+    MK_TRY(gemm(h, "match.dual_softmax", EPI_DUAL, A0, rows, 384, A1, rows, 384, p, st)); }
   return MK_OK;
 }
 
@@ -347,8 +367,8 @@ int run_solve(mk_handle* h, const float* final_scores, const float* kps, const f
   const size_t n_idx = (size_t)n_pairs * c.it_matches * c.num_sampled;
   const int* idx = outer_idx;
   if (!idx) {
-    MK_TRY(sample_outer(final_scores, n_pairs, N, c.it_matches, c.num_sampled, seed, w.samp_ws, w.idx, w.status, st));
-    h->launches += 4;
+    { ProfScope ps_(h, "solve.sample_outer", st); h->launches += 4;
+      MK_TRY(sample_outer(final_scores, n_pairs, N, c.it_matches, c.num_sampled, seed, w.samp_ws, w.idx, w.status, st)); }
     idx = w.idx;
   }
   const float* kps0 = kps;
@@ -356,9 +376,9 @@ int run_solve(mk_handle* h, const float* final_scores, const float* kps, const f
   const float* d0 = depth;
   const float* d1 = depth + (size_t)n_pairs * N;
   int* bs = best_set ? best_set : w.best_hyp;     // scratch when the caller does not want it
-  MK_TRY(ransac_solve(final_scores, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.xyw, w.hyp_scores,
-                      w.hyp_Rt, w.status, pose, bs, inl_mask, best_set ? w.best_hyp : nullptr, st));
-  h->launches += 3;
+  { ProfScope ps_(h, "solve.ransac", st); h->launches += 3;
+    MK_TRY(ransac_solve(final_scores, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.xyw, w.hyp_scores,
+                        w.hyp_Rt, w.status, pose, bs, inl_mask, best_set ? w.best_hyp : nullptr, st)); }
   if (sampled_out) MK_CUDA_CHECK(cudaMemcpyAsync(sampled_out, idx, n_idx * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (hyp_scores_out)
     MK_CUDA_CHECK(cudaMemcpyAsync(hyp_scores_out, w.hyp_scores, (size_t)n_pairs * c.it_matches * c.it_ransac * sizeof(float),
@@ -479,6 +499,38 @@ int mk_forward(mk_handle* h, const float* images, const float* K0, const float* 
 }
 
 long long mk_launch_count(mk_handle* h) { return h ? h->launches : -1; }
+
+int mk_profile_enable(mk_handle* h, int enable) {
+  if (!h) return MK_ERR_INVALID;
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  h->prof.clear();
+  h->profiling = enable != 0;
+  return MK_OK;
+}
+
+// Synchronises the device and writes one line per kernel class: "<tag> <launch scopes> <total ms>\n".
+int mk_profile_read(mk_handle* h, char* buf, int buf_bytes) {
+  if (!h || !buf || buf_bytes <= 0) return MK_ERR_INVALID;
+  MK_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<std::string> order;
+  std::unordered_map<std::string, std::pair<int, double>> acc;
+  for (auto& r : h->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    if (!acc.count(r.tag)) order.push_back(r.tag);
+    acc[r.tag].first += 1;
+    acc[r.tag].second += ms;
+  }
+  std::string out;
+  char line[256];
+  for (auto& t : order) {
+    snprintf(line, sizeof(line), "%s %d %.6f\n", t.c_str(), acc[t].first, acc[t].second);
+    out += line;
+  }
+  if ((int)out.size() + 1 > buf_bytes) { set_last_error("profile buffer too small"); return MK_ERR_INVALID; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return MK_OK;
+}
 
 // ---- operator-level entry points ---------------------------------------------------------------------------------
 int mk_op_gemm(const mk_gemm_args* a, void* stream) {

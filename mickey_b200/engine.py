@@ -247,6 +247,19 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.mk_launch_count(self.h))
 
+    def profile(self, enable: bool):
+        _lib.check(self.lib.mk_profile_enable(self.h, int(enable)), "mk_profile_enable")
+
+    def profile_read(self) -> Dict[str, tuple]:
+        """{kernel class: (launch scopes, total device ms)} measured with CUDA events on the launch stream."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(self.lib.mk_profile_read(self.h, buf, len(buf)), "mk_profile_read")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, n, ms = line.split()
+            out[tag] = (int(n), float(ms))
+        return out
+
     def _ws_for(self, n_pairs, H, W):
         # the workspace layout depends on n_pairs: carve exactly for this call's batch
         self.prepare(n_pairs, H, W)

@@ -1,0 +1,261 @@
+"""GPU unit tests of the individual CUDA kernels (through the operator-level C ABI) against plain
+fp32 torch math on the same inputs.  The tcgen05 GEMM is additionally cross-checked against the SIMT
+debug kernel, which shares its epilogues, to separate descriptor bugs from epilogue bugs."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mickey_b200 import _lib
+from tests.common import rel_err
+from tests.gpu_util import gemm, stream
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("M,N,K", [(300, 256, 192), (128, 128, 64), (1000, 384, 1536), (77, 64, 128)])
+def test_gemm_store_h_bias_gelu(impl, M, N, K):
+    a = _rand(M, K, seed=1).half()
+    w = _rand(N, K, scale=0.05, seed=2).half()
+    bias = _rand(N, scale=0.1, seed=3)
+    out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+    gemm("STORE_H", a, w, M, N, K, impl=impl, bias=bias, act=1, out_h=out, out_h_ld=N)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    assert rel_err(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_gemm_resid_layerscale(impl):
+    M, N, K = 515, 384, 384
+    a = _rand(M, K, seed=4).half()
+    w = _rand(N, K, scale=0.05, seed=5).half()
+    bias, gamma = _rand(N, scale=0.1, seed=6), _rand(N, seed=7)
+    x = _rand(M, N, seed=8)
+    ref = x + gamma * (a.float() @ w.float().t() + bias)
+    gemm("RESID_F", a, w, M, N, K, impl=impl, bias=bias, gamma=gamma, out_f=x, out_f_ld=N)
+    assert rel_err(x, ref) < 1e-5
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_gemm_grouped_store_f(impl):
+    """4 groups reading column slices of one A matrix and row slices of one stacked B (head layout)."""
+    R, G, K, N = 333, 4, 128, 384
+    a = _rand(R, G * 256, seed=9).half()
+    w = _rand(G * N, K, scale=0.1, seed=10).half()
+    out = torch.zeros(R, G * N, device=DEV)
+    gemm("STORE_F", a, w, R, N, K, impl=impl, groups=G, a_col_group_off=256, b_row_group_off=N,
+         out_f=out, out_f_ld=G * N, out_f_group_off=N)
+    for g in range(G):
+        ref = a[:, g * 256:g * 256 + K].float() @ w[g * N:(g + 1) * N].float().t()
+        assert rel_err(out[:, g * N:(g + 1) * N], ref) < 1e-5, g
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("cin,cout", [(128, 64), (192, 128)])
+def test_conv3x3_as_shifted_gemm(impl, cin, cout):
+    """3x3 conv (pad 1) + bias + fp16 residual + ReLU over a zero-padded NHWC image == F.conv2d."""
+    n_img, gh, gw = 3, 9, 7
+    h2, w2 = gh + 2, gw + 2
+    x = _rand(n_img, cin, gh, gw, seed=11).half()
+    wt = _rand(cout, cin, 3, 3, scale=0.05, seed=12).half()
+    bias = _rand(cout, scale=0.1, seed=13)
+    res = _rand(n_img, cout, gh, gw, seed=14).half()
+    xp = torch.zeros(n_img, h2, w2, cin, dtype=torch.float16, device=DEV)
+    xp[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    rp = torch.zeros(n_img, h2, w2, cout, dtype=torch.float16, device=DEV)
+    rp[:, 1:-1, 1:-1] = res.permute(0, 2, 3, 1)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    R = n_img * h2 * w2
+    out = torch.full((R, cout), 7.0, dtype=torch.float16, device=DEV)
+    out32 = torch.full((R, cout), 7.0, device=DEV)
+    taps = [(ky - 1) * w2 + (kx - 1) for ky in range(3) for kx in range(3)]
+    gemm("CONV", xp.reshape(R, cin), wp, R, cout, impl=impl, taps=taps, chunks_per_tap=cin // 64, bias=bias, act=2,
+         res_h=rp.reshape(R, cout), res_h_ld=cout, pad_h2=h2, pad_w2=w2, out_h=out, out_h_ld=cout,
+         out_f=out32, out_f_ld=cout)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), padding=1) + bias.view(1, -1, 1, 1) + res.float())
+    got = out32.reshape(n_img, h2, w2, cout)
+    assert rel_err(got[:, 1:-1, 1:-1].permute(0, 3, 1, 2), ref) < 1e-5
+    ring = got.clone(); ring[:, 1:-1, 1:-1] = 0
+    assert float(ring.abs().max()) == 0.0          # pad ring is written as zeros
+    assert rel_err(out.float(), out32) < 1e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_gemm_layernorm_epilogue(impl):
+    R, G, K = 260, 2, 256
+    a = _rand(R, G * K, seed=15).half()
+    w = _rand(G * 128, K, scale=0.1, seed=16).half()
+    gamma, beta = _rand(G * 128, seed=17), _rand(G * 128, seed=18)
+    x32 = _rand(R, G * 128, seed=19)
+    x_ref = x32.clone()
+    out_h = torch.zeros(R, G * 256, dtype=torch.float16, device=DEV)
+    gemm("LN", a, w, R, 128, K, impl=impl, groups=G, a_col_group_off=K, b_row_group_off=128, gamma=gamma, beta=beta,
+         ln_group_off=128, eps=1e-5, out_f=x32, out_f_ld=G * 128, out_f_group_off=128, out_h=out_h, out_h_ld=G * 256,
+         out_h_group_off=256)
+    for g in range(G):
+        acc = a[:, g * K:(g + 1) * K].float() @ w[g * 128:(g + 1) * 128].float().t()
+        ref = x_ref[:, g * 128:(g + 1) * 128] + F.layer_norm(acc, (128,), gamma[g * 128:(g + 1) * 128],
+                                                               beta[g * 128:(g + 1) * 128], 1e-5)
+        assert rel_err(x32[:, g * 128:(g + 1) * 128], ref) < 1e-4, g
+        assert rel_err(out_h[:, g * 256:g * 256 + 128], ref) < 1e-3, g
+
+
+@pytest.mark.parametrize("D", [384, 768, 1024])
+def test_layernorm(D):
+    lib = _lib.load()
+    rows = 777
+    x, w, b = _rand(rows, D, seed=20) * 3 + 1, _rand(D, seed=21), _rand(D, seed=22)
+    out = torch.zeros(rows, D, dtype=torch.float16, device=DEV)
+    _lib.check(lib.mk_op_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), rows, D, 1e-6, 0, 0, 0, stream()))
+    assert rel_err(out, F.layer_norm(x, (D,), w, b, 1e-6)) < 1e-3
+
+
+def test_layernorm_scatter_to_padded_grid():
+    lib = _lib.load()
+    n_img, gh, gw, D = 2, 5, 4, 384
+    T = gh * gw + 1
+    x, w, b = _rand(n_img * T, D, seed=23), _rand(D, seed=24), _rand(D, seed=25)
+    out = torch.zeros(n_img, gh + 2, gw + 2, D, dtype=torch.float16, device=DEV)
+    _lib.check(lib.mk_op_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), n_img * T, D, 1e-6, 1, gh, gw, stream()))
+    ref = F.layer_norm(x, (D,), w, b, 1e-6).reshape(n_img, T, D)[:, 1:].reshape(n_img, gh, gw, D)
+    assert rel_err(out[:, 1:-1, 1:-1], ref) < 1e-3
+    assert float(out[:, 0].abs().max()) == 0 and float(out[:, :, 0].abs().max()) == 0
+
+
+@pytest.mark.parametrize("T,heads", [(211, 6), (1939, 6), (64, 12)])
+def test_attention(T, heads):
+    lib = _lib.load()
+    n_img, D = 2, heads * 64
+    qkv = (_rand(n_img * T, 3 * D, seed=26) * 1.5).half()
+    out = torch.zeros(n_img * T, D, dtype=torch.float16, device=DEV)
+    _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), n_img, T, D, heads, stream()))
+    q, k, v = qkv.float().reshape(n_img, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(n_img * T, D)
+    assert rel_err(out, ref) < 2e-3
+
+
+def test_patch_gather_and_patch_epilogue():
+    lib = _lib.load()
+    n_img, H, W, D = 2, 70, 56, 384
+    gh, gw = H // 14, W // 14
+    N = gh * gw
+    img = torch.rand(n_img, 3, H, W, device=DEV)
+    wt = _rand(D, 3, 14, 14, scale=0.05, seed=27)
+    posb, clspos = _rand(N, D, seed=28), _rand(D, seed=29)
+    P = torch.zeros(n_img * N, 640, dtype=torch.float16, device=DEV)
+    X = torch.zeros(n_img * (N + 1), D, device=DEV)
+    _lib.check(lib.mk_op_patch_gather(_lib.ptr(img), _lib.ptr(P), n_img, H, W, 640, _lib.ptr(X), _lib.ptr(clspos), D, stream()))
+    wp = F.pad(wt.reshape(D, 588), (0, 52)).half().contiguous()
+    gemm("PATCH", P, wp, n_img * N, D, 640, aux=posb, tok_per_img=N, out_f=X, out_f_ld=D)
+    ref = F.conv2d(img.half().float(), wt.half().float(), stride=14).flatten(2).transpose(1, 2) + posb[None]
+    Xr = X.reshape(n_img, N + 1, D)
+    assert rel_err(Xr[:, 1:], ref) < 1e-5
+    assert rel_err(Xr[:, 0], clspos[None].expand(n_img, -1)) < 1e-7
+
+
+def test_linear_attention():
+    lib = _lib.load()
+    n_img, G, gh, gw = 2, 4, 6, 5
+    h2, w2 = gh + 2, gw + 2
+    R = n_img * h2 * w2
+    qkv = _rand(R, G * 384, seed=30)
+    kv = torch.zeros(n_img, G, 8, 272, device=DEV)
+    msg = torch.zeros(R, G * 128, dtype=torch.float16, device=DEV)
+    _lib.check(lib.mk_op_linattn(_lib.ptr(qkv), _lib.ptr(kv), _lib.ptr(msg), n_img, G, h2, w2, 1e-6, stream()))
+    t = qkv.reshape(n_img, h2, w2, G, 3, 8, 16)[:, 1:-1, 1:-1].reshape(n_img, gh * gw, G, 3, 8, 16)
+    for g in range(G):
+        q, k, v = t[:, :, g, 0], t[:, :, g, 1], t[:, :, g, 2]
+        Q, K = F.elu(q) + 1, F.elu(k) + 1
+        L = gh * gw
+        KV = torch.einsum("bshd,bshv->bhdv", K, v / L)
+        Z = 1 / (torch.einsum("blhd,bhd->blh", Q, K.sum(1)) + 1e-6)
+        ref = torch.einsum("blhd,bhdv,blh->blhv", Q, KV, Z) * L
+        got = msg.reshape(n_img, h2, w2, G, 8, 16)[:, 1:-1, 1:-1, g].reshape(n_img, L, 8, 16)
+        assert rel_err(got, ref) < 2e-3, g
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_matcher_epilogues_vs_dual_softmax(impl):
+    """LSE x2 + DUAL epilogues on split-fp16 descriptors == softmax(dim1)*softmax(dim2) with dustbin."""
+    B, N, T = 2, 300, 0.1
+    d0 = F.normalize(_rand(B, N, 128, seed=31), dim=-1)
+    d1 = F.normalize(_rand(B, N, 128, seed=32), dim=-1)
+    s0, s1 = torch.rand(B, N, device=DEV), torch.rand(B, N, device=DEV)
+    dust = torch.tensor([1.0], device=DEV)
+
+    def split(d, role):
+        hi = d.half()
+        lo = (d - hi.float()).half()
+        return torch.cat([hi, lo, hi] if role == 0 else [hi, hi, lo], dim=-1).reshape(B * N, 384).contiguous()
+
+    a0, a1 = split(d0, 0), split(d1, 1)
+    shift = torch.full((B,), 10.0, device=DEV)
+    rs, cs = torch.zeros(B, N, device=DEV), torch.zeros(B, N, device=DEV)
+    common = dict(groups=B, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=1 / T, shift=shift, dustbin=dust)
+    gemm("LSE", a0, a1, N, N, 384, impl=impl, row_sum=rs, **common)
+    gemm("LSE", a1, a0, N, N, 384, impl=impl, row_sum=cs, **common)
+    sc, kp, fin = (torch.zeros(B, N, N, device=DEV) for _ in range(3))
+    gemm("DUAL", a0, a1, N, N, 384, impl=impl, rs=rs, cs=cs, scr0=s0, scr1=s1, scores=sc, kp_scores=kp,
+         final_scores=fin, **common)
+    S = torch.einsum("bnd,bmd->bnm", d0.double(), d1.double()) / T
+    full = torch.full((B, N + 1, N + 1), 1.0, dtype=torch.float64, device=DEV)
+    full[:, :N, :N] = S
+    ref = (torch.softmax(full, 1) * torch.softmax(full, 2))[:, :N, :N]
+    assert rel_err(sc, ref) < 1e-4
+    assert rel_err(kp, s0[:, :, None] * s1[:, None, :]) < 1e-6
+    assert rel_err(fin, ref * s0[:, :, None].double() * s1[:, None, :].double()) < 1e-4
+
+
+def test_outer_sampler_properties():
+    """Exponential-race sampler: distinct cells, never a zero-probability cell, heavy cells (almost) always
+    drawn, light cells drawn in proportion to their mass."""
+    lib = _lib.load()
+    B, N, IM, n_s = 1, 150, 8, 2048
+    cells = N * N
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(B, cells, generator=g) * 1e-6
+    zero = torch.rand(B, cells, generator=g) < 0.3
+    p[zero] = 0
+    heavy = torch.randperm(cells, generator=g)[:500]
+    p[0, heavy] = 1.0
+    p = p.to(DEV)
+    ws_bytes = lib.mk_op_sample_workspace_bytes(B, IM)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
+    idx = torch.full((B * IM, n_s), -1, dtype=torch.int32, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.check(lib.mk_op_sample(_lib.ptr(p), B, N, IM, n_s, 1234, _lib.ptr(ws), ws_bytes, _lib.ptr(idx), _lib.ptr(status), stream()))
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    idx = idx.long().cpu()
+    pc = p.cpu()[0]
+    heavy_set = set(heavy.tolist())
+    for s in range(IM):
+        row = idx[s]
+        assert row.min() >= 0 and row.max() < cells
+        assert len(set(row.tolist())) == n_s                      # without replacement
+        assert float(pc[row].min()) > 0                           # zero cells are never drawn
+        assert len(heavy_set & set(row.tolist())) == 500          # P(miss) ~ 1e-6 * cells / 1 per heavy cell
+    # streams differ from each other
+    assert len(set(idx[0].tolist()) & set(idx[1].tolist())) < n_s
+    # light cells: inclusion frequency ~ proportional to p (two mass classes, ratio 2)
+    p2 = torch.full((1, cells), 1e-6)
+    p2[0, : cells // 2] = 2e-6
+    p2 = p2.to(DEV)
+    _lib.check(lib.mk_op_sample(_lib.ptr(p2), 1, N, IM, n_s, 99, _lib.ptr(ws), ws_bytes, _lib.ptr(idx := torch.zeros(IM, n_s, dtype=torch.int32, device=DEV)), _lib.ptr(status), stream()))
+    torch.cuda.synchronize()
+    frac_heavy = float((idx.long() < cells // 2).float().mean())
+    assert abs(frac_heavy - 2 / 3) < 0.03, frac_heavy
+    # same seed -> same draw (counter-based generator), different seed -> different draw
+    idx_b = torch.zeros(IM, n_s, dtype=torch.int32, device=DEV)
+    _lib.check(lib.mk_op_sample(_lib.ptr(p2), 1, N, IM, n_s, 99, _lib.ptr(ws), ws_bytes, _lib.ptr(idx_b), _lib.ptr(status), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(idx, idx_b)
