@@ -93,90 +93,104 @@ def work_model(D=384, depth=12, n_pairs=1):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled through NVML DURING the timed region (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; B200_PROFILING.md)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.sm, self.power, self.reasons, self.stop_flag, self.max_sm, self.err = index, [], [], set(), False, None, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.rows.append([x.strip() for x in line.split(",")])
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop_flag:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:          # noqa: BLE001
+            self.err = repr(e)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=2)
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+               "samples": len(sm), "power_w_max": max(self.power) if self.power else None}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+def usable_cpus():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:      # noqa: BLE001
+        pass
+    return n
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_pairs_per_s(n_timed, threads):
+def cpu_threads():
+    # torch CPU kernels at these sizes stop scaling (and then regress badly) past a few dozen threads
+    return min(usable_cpus(), 32)
+
+
+def cpu_reference_run(n_timed, n_warm, threads, budget_s=25.0):
     """The reference's CPU path restated by the oracle (kind 'port': the Python reference cannot travel to
-    the GPU box; oracle/mickey_oracle.py is pinned to it by tests/golden), fp32, all host threads."""
+    the GPU box; oracle/mickey_oracle.py is pinned to it by tests/golden), fp32.  Returns per-pair seconds."""
     from oracle import mickey_oracle as mo
     torch.set_num_threads(threads)
     cfg = mickey_cfg(VARIANT, IT_MATCHES, IT_RANSAC, float16=False)
     sd = synthetic_state_dict(cfg, seed=0)
     im0, im1, K = synthetic_pair(1, seed=0)
-    times = []
+    durs, spent = [], 0.0
     with torch.no_grad():
-        for i in range(1 + n_timed):
+        for i in range(n_warm + n_timed):
             data = {"image0": im0, "image1": im1, "K_color0": K, "K_color1": K}
             torch.manual_seed(i)
             t0 = time.perf_counter()
             mo.model_forward(sd, data, cfg)
-            times.append(time.perf_counter() - t0)
-    timed = times[1:]
-    return len(timed) / sum(timed), sum(timed) / len(timed)
+            dt = time.perf_counter() - t0
+            spent += dt
+            if i >= n_warm:
+                durs.append(dt)
+            if spent > budget_s and durs:
+                break
+    return durs
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    # a "step" is one pair through the CPU path; warm-up steps are run but not timed
-    from oracle import mickey_oracle as mo
-    torch.set_num_threads(threads)
-    cfg = mickey_cfg(VARIANT, IT_MATCHES, IT_RANSAC, float16=False)
-    sd = synthetic_state_dict(cfg, seed=0)
-    im0, im1, K = synthetic_pair(1, seed=0)
-    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    durs = []
-    with torch.no_grad():
-        for i in range(warm + steps):
-            data = {"image0": im0, "image1": im1, "K_color0": K, "K_color1": K}
-            torch.manual_seed(i)
-            t0 = time.perf_counter()
-            mo.model_forward(sd, data, cfg)
-            if i >= warm:
-                durs.append(time.perf_counter() - t0)
+    threads = cpu_threads()
+    # a "step" is one pair through the CPU path; warm-up steps are run but not timed; the run is bounded
+    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 1))
+    durs = cpu_reference_run(steps, warm, threads, budget_s=120.0)
+    steps = len(durs)
     val = len(durs) / sum(durs)
     line = {"impl": "reference", "metric": "image-pairs/sec @720x540", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sum(durs) / len(durs), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "reference CPU path (oracle port of the PyTorch reference), rank 0 only"},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} pairs of the bench workload (steps clamped to 8, warm-up to 2)"},
+                             "sample": f"{steps} pairs of the bench workload (steps clamped to 8 / 120 s, 1 warm-up), "
+                                       f"torch threads = {threads} of {usable_cpus()} usable"},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -208,6 +222,7 @@ def main():
 
     cfg = mickey_cfg(VARIANT, IT_MATCHES, IT_RANSAC)
     model = build_model(cfg, synthetic_checkpoint(cfg, seed=0, with_backbone=True))
+    model.static_outputs = True     # hand out the engine's static output buffers (no per-call clones)
     B = 1
     im0, im1, K = synthetic_pair(B, seed=rank)
     dev_data = {"image0": im0.to(dev), "image1": im1.to(dev), "K_color0": K.to(dev), "K_color1": K.to(dev)}
@@ -259,9 +274,9 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = eng.launch_count
+    l0 = eng.total_kernel_launches
     total_ms = timed(step_device, args.steps)
-    launches = eng.launch_count - l0
+    launches = eng.total_kernel_launches - l0
     clock_info = clocks.finish() if rank == 0 else None
 
     for _ in range(2):
@@ -273,9 +288,11 @@ def main():
     if rank == 0:
         n_prof = 3
         eng.profile(True)
+        model.use_graph = False                 # per-kernel events need eager launches
         for _ in range(n_prof):
             flush.fill_(1)
             model(dict(dev_data))               # no collective here: the other ranks are already done
+        model.use_graph = True
         raw = eng.profile_read()
         eng.profile(False)
         prof = {k: {"scopes_per_step": v[0] / n_prof, "ms_per_step": v[1] / n_prof} for k, v in raw.items()}
@@ -314,7 +331,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tensor core), f32 matcher+solver", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "parallelism": f"dp{world} (pairs sharded, one all-gather of [B,13] poses)",
-                   "l2": "256 MiB buffer written between timed iterations (L2 flushed)", "weights": "seeded random init"},
+                   "l2": "256 MiB buffer written between timed iterations (L2 flushed)", "weights": "seeded random init",
+                   "launch": "one mk_forward C call per step, replayed from a CUDA graph"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(2 * B * 3 * H_IMG * W_IMG * 4), "d2h_bytes_per_step": int(B * 13 * 4)},
         "gpu_launches": int(launches),
@@ -329,10 +347,11 @@ def main():
         "stage_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
     }
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v, sec = cpu_reference_pairs_per_s(n_timed=3, threads=cores)
-        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": f"3 pairs of the same workload after 1 warm-up ({sec:.2f} s/pair), fp32, torch threads = {cores}"}
+        cores = cpu_threads()
+        durs = cpu_reference_run(n_timed=3, n_warm=1, threads=cores, budget_s=25.0)
+        line["cpu_baseline"] = {"value": len(durs) / sum(durs), "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"{len(durs)} pair(s) of the same workload after 1 warm-up ({sum(durs) / len(durs):.2f} s/pair), "
+                                          f"fp32 oracle, torch threads = {cores} of {usable_cpus()} usable"}
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -56,6 +56,9 @@ int mk_set_tensor(mk_handle* h, const char* name, const void* ptr_dev, int dtype
 int mk_finalize(mk_handle* h, int img_h, int img_w);
 
 long long mk_workspace_bytes(mk_handle* h, int n_pairs, int img_h, int img_w);
+/* Byte offset of a named intermediate buffer inside the workspace (debugging / stage-wise tests; names and
+ * layouts are listed in DESIGN.md §3: "X", "F", "CAT", "Y4d", ...). */
+long long mk_workspace_offset(mk_handle* h, const char* name, int n_pairs, int img_h, int img_w);
 
 /* ---- stage 1: feature extraction for 2*n_pairs images
  * replaces MicKey_Extractor.forward (mickey_extractor.py:43-58) for image0 and image1 plus
@@ -78,6 +81,9 @@ int mk_match(mk_handle* h, int n_pairs, float* scores_dev, float* kp_scores_dev,
  * K0/K1 fp32 [n_pairs,3,3].  pose_dev fp32 [n_pairs,13] = R row-major (9) | t (3) | soft inlier count (1).
  * outer_idx_dev int32 [n_pairs*IT_MATCHES, NUM_SAMPLED] / inner_idx_dev int32 [n_pairs*IT_MATCHES*IT_RANSAC, 3]:
  * when non-NULL they replace the two random draws (:231, :251) — the parity tests inject the reference's.
+ * seed: non-zero = (re)seed the solver's counter-based generator; 0 = continue the device-side sequence
+ * (the state lives in device memory and advances after every solve, so a captured CUDA graph of this call
+ * draws fresh numbers on every replay).
  * Optional outputs (NULL to skip): best_set_dev int32 [n_pairs] (index into the IT_MATCHES sampled sets),
  * inlier_mask_dev fp32 [n_pairs, NUM_SAMPLED] (hard inliers of the winning set at the final pose),
  * sampled_idx_out_dev int32 [n_pairs*IT_MATCHES, NUM_SAMPLED] (the cells that were drawn),
@@ -95,6 +101,10 @@ int mk_forward(mk_handle* h, const float* images_dev, const float* K0_dev, const
                float* dsc_dev, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, float* pose_dev,
                int* best_set_dev, float* inlier_mask_dev, int* sampled_idx_out_dev, int* status_dev, void* ws_dev,
                long long ws_bytes, void* stream);
+
+/* (Re)seed the solver's device-side generator on `stream` (used in front of a CUDA-graph replay of mk_forward
+ * captured with seed = 0). */
+int mk_set_seed(mk_handle* h, unsigned long long seed, void* stream);
 
 /* Number of kernel launches issued by this library since the handle was created (for bench.py). */
 long long mk_launch_count(mk_handle* h);

@@ -63,6 +63,7 @@ EXPORTS = {
     "mk_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_longlong]),
     "mk_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mk_workspace_bytes": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mk_workspace_offset": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "mk_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "mk_match": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
@@ -74,6 +75,7 @@ EXPORTS = {
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
                              C.c_void_p]),
     "mk_launch_count": (C.c_longlong, [C.c_void_p]),
+    "mk_set_seed": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     "mk_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "mk_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "mk_op_gemm": (C.c_int, [C.POINTER(MkGemmArgs), C.c_void_p]),

@@ -19,6 +19,7 @@ struct mk_handle {
   std::unordered_map<std::string, Tensor> tensors;
   int geo_h = 0, geo_w = 0;
   bool finalized = false;
+  unsigned long long* seed_dev = nullptr;   // RNG state of the solver (device memory, advanced after every solve)
   long long launches = 0;
   // optional per-kernel-class timing with CUDA events on the launch stream (mk_profile_*)
   bool profiling = false;
@@ -362,13 +363,14 @@ int run_solve(mk_handle* h, const float* final_scores, const float* kps, const f
               float* pose, int* best_set, float* inl_mask, int* sampled_out, float* hyp_scores_out, int* status_out,
               Workspace& w, cudaStream_t st) {
   const mk_config& c = h->cfg;
-  RansacParams rp{c.it_matches, c.it_ransac, c.num_sampled, c.num_corr, c.num_refine, c.th_inlier, c.th_soft_inlier, seed};
+  RansacParams rp{c.it_matches, c.it_ransac, c.num_sampled, c.num_corr, c.num_refine, c.th_inlier, c.th_soft_inlier, h->seed_dev};
+  if (seed != 0) MK_TRY(seed_set(h->seed_dev, seed, st));      // seed == 0: continue the device-side sequence
   MK_CUDA_CHECK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
   const size_t n_idx = (size_t)n_pairs * c.it_matches * c.num_sampled;
   const int* idx = outer_idx;
   if (!idx) {
     { ProfScope ps_(h, "solve.sample_outer", st); h->launches += 4;
-      MK_TRY(sample_outer(final_scores, n_pairs, N, c.it_matches, c.num_sampled, seed, w.samp_ws, w.idx, w.status, st)); }
+      MK_TRY(sample_outer(final_scores, n_pairs, N, c.it_matches, c.num_sampled, h->seed_dev, w.samp_ws, w.idx, w.status, st)); }
     idx = w.idx;
   }
   const float* kps0 = kps;
@@ -379,6 +381,7 @@ int run_solve(mk_handle* h, const float* final_scores, const float* kps, const f
   { ProfScope ps_(h, "solve.ransac", st); h->launches += 3;
     MK_TRY(ransac_solve(final_scores, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.xyw, w.hyp_scores,
                         w.hyp_Rt, w.status, pose, bs, inl_mask, best_set ? w.best_hyp : nullptr, st)); }
+  MK_TRY(seed_advance(h->seed_dev, st));
   if (sampled_out) MK_CUDA_CHECK(cudaMemcpyAsync(sampled_out, idx, n_idx * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (hyp_scores_out)
     MK_CUDA_CHECK(cudaMemcpyAsync(hyp_scores_out, w.hyp_scores, (size_t)n_pairs * c.it_matches * c.it_ransac * sizeof(float),
@@ -432,11 +435,22 @@ int mk_create(int device, const mk_config* cfg, mk_handle** out) {
   mk_handle* h = new mk_handle();
   h->device = device;
   h->cfg = *cfg;
+  MK_CUDA_CHECK(cudaSetDevice(device));
+  MK_CUDA_CHECK(cudaMalloc(&h->seed_dev, sizeof(unsigned long long)));
+  const unsigned long long s0 = 0x243F6A8885A308D3ull;
+  MK_CUDA_CHECK(cudaMemcpy(h->seed_dev, &s0, sizeof(s0), cudaMemcpyHostToDevice));
   *out = h;
   return MK_OK;
 }
 
-int mk_destroy(mk_handle* h) { delete h; return MK_OK; }
+int mk_destroy(mk_handle* h) {
+  if (h) {
+    if (h->seed_dev) cudaFree(h->seed_dev);
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    delete h;
+  }
+  return MK_OK;
+}
 
 int mk_set_tensor(mk_handle* h, const char* name, const void* ptr, int dtype, long long numel) {
   if (!h || !name || !ptr) { set_last_error("null argument"); return MK_ERR_INVALID; }
@@ -499,6 +513,28 @@ int mk_forward(mk_handle* h, const float* images, const float* K0, const float* 
 }
 
 long long mk_launch_count(mk_handle* h) { return h ? h->launches : -1; }
+
+int mk_set_seed(mk_handle* h, unsigned long long seed, void* stream) {
+  if (!h) return MK_ERR_INVALID;
+  return seed_set(h->seed_dev, seed, (cudaStream_t)stream);
+}
+
+long long mk_workspace_offset(mk_handle* h, const char* name, int n_pairs, int H, int W) {
+  if (!h || !name) return -1;
+  const Geo g = make_geo(n_pairs, H, W);
+  uint8_t* base = reinterpret_cast<uint8_t*>(0x1000);     // fake base: only differences are used
+  Workspace w = carve(base, h->cfg, g, n_pairs);
+  const std::unordered_map<std::string, const void*> m = {
+      {"P", w.P}, {"X", w.X}, {"XN", w.XN}, {"QKV", w.QKV}, {"ATT", w.ATT}, {"H1", w.H1}, {"F", w.F}, {"T1", w.T1},
+      {"S1", w.S1}, {"O1", w.O1}, {"T2", w.T2}, {"S2", w.S2}, {"O2", w.O2}, {"T3", w.T3}, {"S3", w.S3}, {"CAT", w.CAT},
+      {"MSG", w.MSG}, {"HM", w.HM}, {"T4k", w.T4k}, {"S4k", w.S4k}, {"T4d", w.T4d}, {"X32", w.X32}, {"QKV32", w.QKV32},
+      {"KV", w.KV}, {"Y4k", w.Y4k}, {"Y4d", w.Y4d}, {"score_raw", w.score_raw}, {"DSCX", w.DSCX}, {"nrm2", w.nrm2},
+      {"row_sum", w.row_sum}, {"col_sum", w.col_sum}, {"idx", w.idx}, {"xyw", w.xyw}, {"hyp_scores", w.hyp_scores},
+      {"hyp_Rt", w.hyp_Rt}};
+  auto it = m.find(name);
+  if (it == m.end()) { set_last_error("unknown workspace buffer '%s'", name); return -1; }
+  return (long long)(reinterpret_cast<const uint8_t*>(it->second) - base);
+}
 
 int mk_profile_enable(mk_handle* h, int enable) {
   if (!h) return MK_ERR_INVALID;
@@ -568,12 +604,16 @@ int mk_op_linattn(const float* qkv, float* kv, void* msg, int n_img, int Gn, int
   MK_TRY(linattn_kv(qkv, kv, n_img, Gn, h2, w2, (cudaStream_t)stream));
   return linattn_msg(qkv, kv, msg, n_img, Gn, h2, w2, eps, (cudaStream_t)stream);
 }
-long long mk_op_sample_workspace_bytes(int B, int IM) { return (long long)sampler_workspace_bytes(B, IM); }
+long long mk_op_sample_workspace_bytes(int B, int IM) { return (long long)sampler_workspace_bytes(B, IM) + 512; }
 int mk_op_sample(const float* fs, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
                  long long ws_bytes, int* idx_out, int* status, void* stream) {
-  if ((long long)sampler_workspace_bytes(B, IM) > ws_bytes) { set_last_error("sampler workspace too small"); return MK_ERR_INVALID; }
+  if ((long long)sampler_workspace_bytes(B, IM) + 256 > ws_bytes) { set_last_error("sampler workspace too small"); return MK_ERR_INVALID; }
   MK_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), (cudaStream_t)stream));
-  return sample_outer(fs, B, N, IM, n_sample, seed, ws, idx_out, status, (cudaStream_t)stream);
+  // the seed word lives at the (256-byte aligned) end of the caller's workspace
+  const size_t off = ((size_t)sampler_workspace_bytes(B, IM) + 255) & ~(size_t)255;
+  unsigned long long* sd = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + off);
+  MK_TRY(seed_set(sd, seed, (cudaStream_t)stream));
+  return sample_outer(fs, B, N, IM, n_sample, sd, ws, idx_out, status, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -7,7 +7,17 @@
 
 namespace mk {
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (reference layers/mlp.py:23 nn.GELU()): erf by Abramowitz-Stegun 7.1.26, |abs err| < 1.5e-7
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == ACT_GELU) return gelu_erf(x);
@@ -32,6 +42,14 @@ __device__ __forceinline__ void store_h32(__half* dst, const float* v) {
   }
 }
 
+__device__ __forceinline__ void add_vec32(float (&v)[32], const float* __restrict__ b) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(b) + q);
+    v[q * 4 + 0] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+  }
+}
+
 __device__ __forceinline__ bool pad_valid(const GemmParams& p, int m, int& pos) {
   const int per_img = p.pad_h2 * p.pad_w2;
   pos = m % per_img;
@@ -44,13 +62,14 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int g, int m, int n0, float (&v)[32]) {
   if constexpr (EPI == EPI_STORE_H) {
     if (m >= p.M) return;
-    if (p.bias) {
-      const float* b = p.bias + (size_t)g * p.bias_group_off + n0;
+    if (p.bias) add_vec32(v, p.bias + (size_t)g * p.bias_group_off + n0);
+    if (p.act == ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += __ldg(b + j);
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
     store_h32(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + n0, v);
   } else if constexpr (EPI == EPI_RESID_F) {
     if (m >= p.M) return;
@@ -82,11 +101,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int g, int m
     if (m >= p.M) return;
     int pos = 0;
     const bool valid = p.pad_h2 ? pad_valid(p, m, pos) : true;
-    if (p.bias) {
-      const float* b = p.bias + (size_t)g * p.bias_group_off + n0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += __ldg(b + j);
-    }
+    if (p.bias) add_vec32(v, p.bias + (size_t)g * p.bias_group_off + n0);
     if (p.res_h) {
       const uint4* r = reinterpret_cast<const uint4*>(p.res_h + (size_t)g * p.res_h_group_off + (size_t)m * p.res_h_ld + n0);
 #pragma unroll
@@ -103,11 +118,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int g, int m
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-    if (p.aux && ((p.aux_group_mask >> g) & 1)) {
-      const float* a = p.aux + (size_t)pos * p.N + n0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += __ldg(a + j);
-    }
+    if (p.aux && ((p.aux_group_mask >> g) & 1)) add_vec32(v, p.aux + (size_t)pos * p.N + n0);
     if (!valid) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.0f;
@@ -125,28 +136,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int g, int m
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-  } else if constexpr (EPI == EPI_DUAL) {
-    if (m >= p.n_valid) return;
-    const float L2E = 1.4426950408889634f;
-    const float sh = __ldg(p.shift + g) * L2E;
-    const float dust = p.dustbin ? exp2f(__ldg(p.dustbin) * L2E - sh) : 0.0f;
-    const size_t gv = (size_t)g * p.n_valid;
-    const float inv_r = 1.0f / (__ldg(p.rs + gv + m) + dust);
-    const float s0 = __ldg(p.scr0 + gv + m);
-    const size_t base = (gv + m) * (size_t)p.n_valid + n0;
-    const float k2 = p.inv_temp * L2E;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int n = n0 + j;
-      if (n < p.n_valid) {
-        const float e = exp2f(fmaf(v[j], k2, -sh));
-        const float sc = (e * inv_r) * (e / (__ldg(p.cs + gv + n) + dust));
-        const float kp = s0 * __ldg(p.scr1 + gv + n);
-        p.scores[base + j] = sc;
-        p.kp_scores[base + j] = kp;
-        p.final_scores[base + j] = sc * kp;
-      }
-    }
   }
 }
 
@@ -161,6 +150,46 @@ __device__ __forceinline__ float lse_partial(const GemmParams& p, int g, int n0,
   for (int j = 0; j < 32; ++j)
     if (n0 + j < p.n_valid) s += exp2f(fmaf(v[j], k2, -sh));
   return s;
+}
+
+// EPI_DUAL, coalesced: the warp owns rows row0..row0+31 (lane == row on entry) and columns n0..n0+31.
+// Each lane scales its row by the row statistics, the 32x32 block is transposed through `stage`
+// ([32][33] floats, warp-private), then lane == column applies the column statistics and every store
+// instruction writes one contiguous 128-byte segment of a row of scores / kp_scores / final_scores.
+__device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int row0, int lane, int n0,
+                                                 const float (&v)[32], float* stage) {
+  const float L2E = 1.4426950408889634f;
+  const float sh = __ldg(p.shift + g) * L2E;
+  const float dust = p.dustbin ? exp2f(__ldg(p.dustbin) * L2E - sh) : 0.0f;
+  const size_t gv = (size_t)g * p.n_valid;
+  const int my_row = row0 + lane;
+  const bool row_ok = my_row < p.n_valid;
+  const float inv_r = row_ok ? 1.0f / (__ldg(p.rs + gv + my_row) + dust) : 0.0f;
+  const float s0 = row_ok ? __ldg(p.scr0 + gv + my_row) : 0.0f;
+  const float k2 = p.inv_temp * L2E;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float e = exp2f(fmaf(v[j], k2, -sh));
+    stage[lane * 33 + j] = e * e * inv_r;
+  }
+  __syncwarp();
+  const int col = n0 + lane;
+  const bool col_ok = col < p.n_valid;
+  const float inv_c = col_ok ? 1.0f / (__ldg(p.cs + gv + col) + dust) : 0.0f;
+  const float s1 = col_ok ? __ldg(p.scr1 + gv + col) : 0.0f;
+  const int rows = min(32, p.n_valid - row0);
+#pragma unroll 4
+  for (int r = 0; r < rows; ++r) {
+    const float sc = stage[r * 33 + lane] * inv_c;
+    const float kp = __shfl_sync(0xffffffffu, s0, r) * s1;
+    if (col_ok) {
+      const size_t o = (gv + row0 + r) * (size_t)p.n_valid + col;
+      p.scores[o] = sc;
+      p.kp_scores[o] = kp;
+      p.final_scores[o] = sc * kp;
+    }
+  }
+  __syncwarp();
 }
 
 // EPI_LN: normalise the 128-wide row (N == 128 == tile width), then optional residual add.

@@ -88,7 +88,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(128)
 gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, const __half* __restrict__ B,
                  long long b_rows, long long ldb, const GemmParams p) {
-  __shared__ __half As[BLOCK_M][BLOCK_K + 8];
+  __shared__ __align__(16) __half As[BLOCK_M][BLOCK_K + 8];
   __shared__ __half Bs[BN][BLOCK_K + 8];
   const int g = blockIdx.z, m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BN;
   const int t = threadIdx.x;
@@ -139,6 +139,14 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
       s += lse_partial(p, g, n0 + c * 32, v);
     }
     if (m < p.n_valid) atomicAdd(p.row_sum + (size_t)g * p.n_valid + m, s);
+  } else if constexpr (EPI == EPI_DUAL) {
+    float* stage = reinterpret_cast<float*>(&As[0][0]) + (t >> 5) * (32 * 33);   // tiles are idle now
+    for (int c = 0; c < BN / 32; ++c) {
+      if (n0 + c * 32 < p.n_valid) {
+        for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
+        dual_store_chunk(p, g, m0 + (t >> 5) * 32, t & 31, n0 + c * 32, v, stage);
+      }
+    }
   } else {
     for (int c = 0; c < BN / 32; ++c) {
       if (n0 + c * 32 < p.N) {

@@ -207,9 +207,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+  }
+  __syncwarp();
+
+  // ===== epilogue: TMEM -> registers -> global, by ALL 8 warps =====
+  // warp w may read TMEM lanes 32*(w%4)..+31 (its quadrant); warps w and w+4 share a quadrant and split the
+  // tile's 32-column chunks between them.  The producer / MMA warps join once their loops have drained.
+  {
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    constexpr int CHUNKS = BN / 32;
+    constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
+    const int c_begin = half * CPH;
+    const int c_end = (c_begin + CPH < CHUNKS) ? c_begin + CPH : CHUNKS;
     const int row = q * 32 + lane;
     const int m = m0 + row;
     mbar_wait(tmem_full_bar, 0);
@@ -219,7 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == EPI_LN) {
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         tmem_ld32(taddr + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum += v[j];
@@ -227,28 +237,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float mean = sum * (1.0f / BN);
       float sq = 0.f;
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         tmem_ld32(taddr + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq += d * d; }
       }
       const float rstd = rsqrtf(sq * (1.0f / BN) + p.eps);
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         tmem_ld32(taddr + c * 32, v);
         ln_store_chunk(p, g, m, n0 + c * 32, v, mean, rstd);
       }
     } else if constexpr (EPI == EPI_LSE) {
       float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         tmem_ld32(taddr + c * 32, v);
         s += lse_partial(p, g, n0 + c * 32, v);
       }
       if (m < p.n_valid) atomicAdd(p.row_sum + (size_t)g * p.n_valid + m, s);
+    } else if constexpr (EPI == EPI_DUAL) {
+      // per-warp 32x33 fp32 staging tile in the (now idle) pipeline smem: transposes "thread == row" into
+      // "lane == column" so that every store instruction writes one contiguous 128-byte row segment
+      float* stage = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * 33);
+      for (int c = c_begin; c < c_end; ++c) {
+        if (n0 + c * 32 < p.n_valid) {
+          tmem_ld32(taddr + c * 32, v);
+          dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage);
+        }
+      }
     } else {
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         if (n0 + c * 32 < p.N) {
           tmem_ld32(taddr + c * 32, v);
           epilogue_chunk<EPI>(p, g, m, n0 + c * 32, v);

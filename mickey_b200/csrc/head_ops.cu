@@ -17,47 +17,52 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v + 1.0f : exp
 // ------------------------------------------------------------------------------------------------------
 // Linear attention, reduction half (reference att_layers/attention.py:55-61):
 //   K = elu(k)+1;  KV[h] = sum_s K[s,h,:]^T (v[s,h,:] / L);  Ksum[h] = sum_s K[s,h,:]
-// qkv fp32 [R, G*384] (q|k|v per group, 8 heads x 16).  out fp32 [n_img, G, 8, 272] (256 KV + 16 Ksum).
-// grid (8, G, n_img), 256 threads: thread (d, v) owns KV[d][v].
+// qkv fp32 [R, G*384] (q|k|v per group, 8 heads x 16).  out fp32 [n_img, G, 8, 272] (256 KV + 16 Ksum),
+// zeroed by the launcher and accumulated with atomics.
+// grid (row chunks of 32, G, n_img), 256 threads: thread t owns head h = t/32, key dim d = (t%32)/2 and eight
+// value dims; the chunk's k and v rows of all 8 heads are staged in shared memory once.
 // ------------------------------------------------------------------------------------------------------
+constexpr int KV_ROWS = 32;
 __global__ void __launch_bounds__(256)
 linattn_kv_kernel(const float* __restrict__ qkv, float* __restrict__ kvout, int G, int h2, int w2) {
-  __shared__ float Ks[64][17];
-  __shared__ float Vs[64][17];
-  const int head = blockIdx.x, g = blockIdx.y, im = blockIdx.z;
+  __shared__ float Ks[KV_ROWS][128 + 4];
+  __shared__ float Vs[KV_ROWS][128 + 4];
+  const int g = blockIdx.y, im = blockIdx.z;
   const int per_img = h2 * w2;
   const float inv_len = 1.0f / (float)((h2 - 2) * (w2 - 2));
-  const int t = threadIdx.x, d = t >> 4, vv = t & 15;
+  const int t = threadIdx.x;
   const long long ld = (long long)G * 384;
-  const float* base = qkv + (long long)im * per_img * ld + g * 384 + head * 16;
-  float acc = 0.f, ksum = 0.f;
-  for (int r0 = 0; r0 < per_img; r0 += 64) {
-    // 64 rows x 16 k-values and 16 v-values: 2048 elements over 256 threads
-    for (int i = t; i < 64 * 16; i += 256) {
-      const int r = i >> 4, c = i & 15;
-      const int pos = r0 + r;
-      int y, x;
-      float kval = 0.f, vval = 0.f;
-      if (pos < per_img && pos_valid(pos, h2, w2, y, x)) {
-        const float* row = base + (long long)pos * ld;
-        kval = elu1(row[128 + c]);
-        vval = row[256 + c] * inv_len;
-      }
-      Ks[r][c] = kval;
-      Vs[r][c] = vval;
+  const float* base = qkv + (long long)im * per_img * ld + g * 384;
+  const int r0 = blockIdx.x * KV_ROWS;
+  // 32 rows x (128 k + 128 v) floats = 2048 float4 over 256 threads
+  for (int i = t; i < KV_ROWS * 64; i += 256) {
+    const int r = i >> 6, c4 = i & 63;           // c4 < 32: k, else v
+    const int pos = r0 + r;
+    int y, x;
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos < per_img && pos_valid(pos, h2, w2, y, x)) {
+      val = *reinterpret_cast<const float4*>(base + (long long)pos * ld + 128 + c4 * 4);
+      if (c4 < 32) { val.x = elu1(val.x); val.y = elu1(val.y); val.z = elu1(val.z); val.w = elu1(val.w); }
+      else { val.x *= inv_len; val.y *= inv_len; val.z *= inv_len; val.w *= inv_len; }
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < 64; ++r) {
-      const float kk = Ks[r][d];
-      acc = fmaf(kk, Vs[r][vv], acc);
-      if (vv == 0) ksum += kk;
-    }
-    __syncthreads();
+    float* dst = (c4 < 32) ? &Ks[r][c4 * 4] : &Vs[r][(c4 - 32) * 4];
+    dst[0] = val.x; dst[1] = val.y; dst[2] = val.z; dst[3] = val.w;
+  }
+  __syncthreads();
+  const int head = t >> 5, d = (t & 31) >> 1, vh = (t & 1) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float ksum = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < KV_ROWS; ++r) {
+    const float kk = Ks[r][head * 16 + d];
+    ksum += kk;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(kk, Vs[r][head * 16 + vh + j], acc[j]);
   }
   float* o = kvout + (((long long)im * G + g) * 8 + head) * 272;
-  o[d * 16 + vv] = acc;
-  if (vv == 0) o[256 + d] = ksum;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(o + d * 16 + vh + j, acc[j]);
+  if (vh == 0) atomicAdd(o + 256 + d, ksum);
 }
 
 // Linear attention, query half (attention.py:52,60-61): msg = (Q KV) / (Q . Ksum + eps) * L, Q = elu(q)+1.
@@ -106,7 +111,8 @@ linattn_msg_kernel(const float* __restrict__ qkv, const float* __restrict__ kv, 
 }
 
 int linattn_kv(const float* qkv, float* kv, int n_img, int G, int h2, int w2, cudaStream_t s) {
-  linattn_kv_kernel<<<dim3(8, G, n_img), 256, 0, s>>>(qkv, kv, G, h2, w2);
+  MK_CUDA_CHECK(cudaMemsetAsync(kv, 0, (size_t)n_img * G * 8 * 272 * sizeof(float), s));
+  linattn_kv_kernel<<<dim3(ceil_div(h2 * w2, KV_ROWS), G, n_img), 256, 0, s>>>(qkv, kv, G, h2, w2);
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }

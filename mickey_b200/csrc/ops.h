@@ -23,10 +23,12 @@ int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float*
 struct RansacParams {
   int it_matches, it_ransac, n_sample, n_corr, n_refine;
   float th_inlier, th_soft;
-  unsigned long long seed;
+  const unsigned long long* seed;     // device pointer
 };
+int seed_set(unsigned long long* s, unsigned long long v, cudaStream_t st);
+int seed_advance(unsigned long long* s, cudaStream_t st);
 size_t sampler_workspace_bytes(int B, int IM);
-int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
+int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, const unsigned long long* seed, void* ws,
                  int* idx_out, int* status, cudaStream_t st);
 int ransac_solve(const float* final_scores, const float* kps0, const float* d0, const float* kps1, const float* d1,
                  const float* K0, const float* K1, int B, int N, const RansacParams& rp, const int* outer_idx,

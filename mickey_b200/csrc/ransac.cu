@@ -50,14 +50,14 @@ constexpr int SAMP_ELEMS_PER_BLOCK = 256 * 32;
 // ---- pass A: histogram ------------------------------------------------------------------------------------
 // grid (blocks over N*N, ceil(IM/4), B); one Philox call per cell yields the noise of 4 streams.
 __global__ void __launch_bounds__(SAMP_THREADS)
-sampler_hist_kernel(const float* __restrict__ fs, long long cells, int IM, unsigned long long seed,
+sampler_hist_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
                     unsigned int* __restrict__ hist) {
   __shared__ unsigned int h[4][HBINS];
   for (int i = threadIdx.x; i < 4 * HBINS; i += SAMP_THREADS) (&h[0][0])[i] = 0;
   __syncthreads();
   const int sg = blockIdx.y, b = blockIdx.z;
   const float* p = fs + (long long)b * cells;
-  const Philox rng(seed);
+  const Philox rng(*seed_ptr);
   const long long e0 = (long long)blockIdx.x * SAMP_ELEMS_PER_BLOCK;
   const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
   for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) {
@@ -80,32 +80,45 @@ sampler_hist_kernel(const float* __restrict__ fs, long long cells, int IM, unsig
   }
 }
 
-// threshold bin per stream: largest T with count(bin >= T) >= n_sample.  one warp per stream.
-__global__ void sampler_threshold_kernel(const unsigned int* __restrict__ hist, int n_streams, int n_sample,
-                                         int* __restrict__ thr, int* __restrict__ status) {
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (s >= n_streams) return;
+// threshold bin per stream: largest T with count(bin >= T) >= n_sample.  one 256-thread block per stream:
+// thread t owns the 8 bins [8t, 8t+8); a block-wide suffix sum locates the crossing.
+__global__ void __launch_bounds__(256)
+sampler_threshold_kernel(const unsigned int* __restrict__ hist, int n_streams, int n_sample, int* __restrict__ thr,
+                         int* __restrict__ status) {
+  __shared__ unsigned int wsum[8];
+  __shared__ int found;
+  const int s = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const unsigned int* h = hist + (long long)s * HBINS;
-  unsigned int above = 0;
-  int T = -1;
-  for (int base = HBINS - 32; base >= 0 && T < 0; base -= 32) {
-    const unsigned int c = h[base + lane];
-    // inclusive suffix sum within the 32 bins (lane 31 = highest bin)
-    unsigned int suf = c;
+  unsigned int c[8];
+  unsigned int mine = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int v = __shfl_down_sync(0xffffffffu, suf, o);
-      if (lane + o < 32) suf += v;
-    }
-    const unsigned int tot = __shfl_sync(0xffffffffu, suf, 0);
-    const unsigned int ballot = __ballot_sync(0xffffffffu, above + suf >= (unsigned)n_sample);
-    if (ballot) {
-      T = base + (31 - __clz(ballot));     // highest bin whose suffix count reaches n_sample
-    } else {
-      above += tot;
-    }
+  for (int j = 0; j < 8; ++j) { c[j] = h[t * 8 + j]; mine += c[j]; }
+  if (t == 0) found = -1;
+  // inclusive suffix sum over threads (thread 255 = highest bins)
+  unsigned int suf = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += v;
   }
-  if (lane == 0) {
+  if (lane == 0) wsum[warp] = suf;
+  __syncthreads();
+  unsigned int above_warp = 0;
+  for (int w = warp + 1; w < 8; ++w) above_warp += wsum[w];
+  const unsigned int incl = suf + above_warp;          // count of bins >= 8t
+  const unsigned int excl = incl - mine;               // count of bins >= 8(t+1)
+  if (incl >= (unsigned)n_sample && excl < (unsigned)n_sample) {
+    unsigned int run = excl;
+    int T = t * 8;
+    for (int j = 7; j >= 0; --j) {
+      run += c[j];
+      if (run >= (unsigned)n_sample) { T = t * 8 + j; break; }
+    }
+    found = T;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int T = found;
     // bin 0 holds the zero-probability cells (key 0): they may never be drawn (ATen raises in that case and
     // the reference's try/except returns the zero pose, probabilisticProcrustes.py:331-342)
     if (T <= 0) { T = 1; atomicOr(status, 1); }
@@ -115,12 +128,12 @@ __global__ void sampler_threshold_kernel(const unsigned int* __restrict__ hist, 
 
 // ---- pass B: collect candidates (bin >= threshold) ---------------------------------------------------------
 __global__ void __launch_bounds__(SAMP_THREADS)
-sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, unsigned long long seed,
+sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
                        const int* __restrict__ thr, unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt,
                        int cap) {
   const int sg = blockIdx.y, b = blockIdx.z;
   const float* p = fs + (long long)b * cells;
-  const Philox rng(seed);
+  const Philox rng(*seed_ptr);
   int T[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) T[j] = (sg * 4 + j < IM) ? thr[(long long)b * IM + sg * 4 + j] : 0x7fffffff;
@@ -156,12 +169,15 @@ sampler_select_kernel(const unsigned long long* __restrict__ cand, const unsigne
     if (n_raw > (unsigned)CAP) atomicOr(status, 2);     // candidate buffer overflow (selection truncated)
     if (n < n_sample) atomicOr(status, 1);
   }
-  for (int i = threadIdx.x; i < CAP; i += 1024) keys[i] = (i < n) ? cand[s * CAP + i] : 0ull;
+  // sort only the power of two that holds the candidates (typically ~2.3 k of them -> 4096)
+  int SZ = 2048;
+  while (SZ < n) SZ <<= 1;
+  for (int i = threadIdx.x; i < SZ; i += 1024) keys[i] = (i < n) ? cand[s * CAP + i] : 0ull;
   __syncthreads();
   // bitonic sort, descending
-  for (int k = 2; k <= CAP; k <<= 1) {
+  for (int k = 2; k <= SZ; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < CAP; i += 1024) {
+      for (int i = threadIdx.x; i < SZ; i += 1024) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long a = keys[i], c = keys[ixj];
@@ -182,7 +198,7 @@ size_t sampler_workspace_bytes(int B, int IM) {
   return streams * HBINS * 4 + streams * 4 /*thr*/ + streams * 4 /*cnt*/ + streams * CAND_CAP * 8 + 256;
 }
 
-int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
+int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, const unsigned long long* seed, void* ws,
                  int* idx_out, int* status, cudaStream_t st) {
   if (n_sample > CAND_CAP / 2) { set_last_error("NUM_SAMPLED_MATCHES %d too large", n_sample); return MK_ERR_UNSUPPORTED; }
   const long long cells = (long long)N * N;
@@ -197,7 +213,7 @@ int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, 
   dim3 grid((unsigned)((cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK), ceil_div(IM, 4), B);
   sampler_hist_kernel<<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, hist);
   MK_CUDA_CHECK(cudaGetLastError());
-  sampler_threshold_kernel<<<ceil_div((int)streams, 4), 128, 0, st>>>(hist, (int)streams, n_sample, thr, status);
+  sampler_threshold_kernel<<<(unsigned)streams, 256, 0, st>>>(hist, (int)streams, n_sample, thr, status);
   MK_CUDA_CHECK(cudaGetLastError());
   sampler_collect_kernel<<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, cand, cnt, CAND_CAP);
   MK_CUDA_CHECK(cudaGetLastError());
@@ -353,7 +369,7 @@ __device__ __forceinline__ int cdf_search(const float* cdf, int n, float target)
 // grid (groups of hypotheses, IM, B).  smem: X[3][n_s] Y[3][n_s] cdf[n_s]
 __global__ void __launch_bounds__(HYP_THREADS)
 ransac_hyp_kernel(const float* __restrict__ xyw, const int* __restrict__ inner_idx, int IM, int IR, int n_s,
-                  int hyp_per_block, float th_soft, unsigned long long seed, float* __restrict__ scores,
+                  int hyp_per_block, float th_soft, const unsigned long long* __restrict__ seed_ptr, float* __restrict__ scores,
                   float* __restrict__ Rt, int* __restrict__ status) {
   extern __shared__ float sm[];
   float* X = sm;                 // [3][n_s]
@@ -382,7 +398,7 @@ ransac_hyp_kernel(const float* __restrict__ xyw, const int* __restrict__ inner_i
   __syncthreads();
   const float W = cdf[n_s - 1];
   const float beta = 5.0f / th_soft;
-  const Philox rng(seed ^ 0x9E3779B97F4A7C15ull);
+  const Philox rng(*seed_ptr ^ 0x9E3779B97F4A7C15ull);
 
   const int h0 = blockIdx.x * hyp_per_block;
   for (int hh = warp; hh < hyp_per_block; hh += HYP_THREADS / 32) {
@@ -586,6 +602,25 @@ ransac_finalize_kernel(const float* __restrict__ xyw, const float* __restrict__ 
     best_set[b] = sset;
     if (best_hyp) best_hyp[b] = best;
   }
+}
+
+// seed state lives in device memory so that a captured CUDA graph draws fresh numbers on every replay
+__global__ void seed_set_kernel(unsigned long long* s, unsigned long long v) { *s = v; }
+__global__ void seed_advance_kernel(unsigned long long* s) {
+  unsigned long long z = *s + 0x9E3779B97F4A7C15ull;          // splitmix64 step
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  *s = z ^ (z >> 31);
+}
+int seed_set(unsigned long long* s, unsigned long long v, cudaStream_t st) {
+  seed_set_kernel<<<1, 1, 0, st>>>(s, v);
+  MK_CUDA_CHECK(cudaGetLastError());
+  return MK_OK;
+}
+int seed_advance(unsigned long long* s, cudaStream_t st) {
+  seed_advance_kernel<<<1, 1, 0, st>>>(s);
+  MK_CUDA_CHECK(cudaGetLastError());
+  return MK_OK;
 }
 
 int ransac_solve(const float* final_scores, const float* kps0, const float* d0, const float* kps1, const float* d1,

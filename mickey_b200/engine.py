@@ -245,7 +245,25 @@ class Engine:
 
     @property
     def launch_count(self) -> int:
+        """Kernel launches issued by the library (eager calls) ..."""
         return int(self.lib.mk_launch_count(self.h))
+
+    @property
+    def total_kernel_launches(self) -> int:
+        """... plus the kernel nodes executed by CUDA-graph replays of mk_forward."""
+        return self.launch_count + getattr(self, "graph_launches", 0)
+
+    def ws_view(self, name: str, dtype, shape):
+        """Typed view of a named intermediate buffer of the last call's workspace (debugging / tests)."""
+        H, W = self.geo
+        off = self.lib.mk_workspace_offset(self.h, name.encode(), self.ws_pairs, H, W)
+        if off < 0:
+            raise _lib.MickeyB200Error(self.lib.mk_last_error().decode())
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.ws[off:off + nbytes].view(dtype).reshape(shape)
 
     def profile(self, enable: bool):
         _lib.check(self.lib.mk_profile_enable(self.h, int(enable)), "mk_profile_enable")
@@ -306,6 +324,72 @@ class Engine:
         _lib.check(self.lib.mk_match(self.h, B, _lib.ptr(scores), _lib.ptr(kp_scores), _lib.ptr(final),
                                      _lib.ptr(self.ws), self.ws.numel(), self._stream()), "mk_match")
         return scores, kp_scores, final
+
+    # -- whole path in one C call, optionally replayed from a CUDA graph -------------------------------------------
+    def _static_buffers(self, B, H, W):
+        dev, c = self.device, self.mkcfg
+        N = (H // PATCH) * (W // PATCH)
+        f = lambda *s: torch.empty(*s, device=dev)                       # noqa: E731
+        return {
+            "images": f(2 * B, 3, H, W), "K0": f(B, 3, 3), "K1": f(B, 3, 3),
+            "kps": f(2 * B, 2, N), "depth": f(2 * B, 1, N), "scr": f(2 * B, 1, N), "dsc": f(2 * B, c.desc_dim, N),
+            "scores": f(B, N, N), "kp_scores": f(B, N, N), "final_scores": f(B, N, N), "pose": f(B, 13),
+            "best_set": torch.empty(B, dtype=torch.int32, device=dev), "inlier_mask": f(B, c.num_sampled),
+            "sampled_idx": torch.empty(B * c.it_matches, c.num_sampled, dtype=torch.int32, device=dev),
+            "status": torch.zeros(1, dtype=torch.int32, device=dev),
+        }
+
+    def _call_forward(self, st, B, H, W, seed):
+        ws = self.ws
+        _lib.check(self.lib.mk_forward(
+            self.h, _lib.ptr(st["images"]), _lib.ptr(st["K0"]), _lib.ptr(st["K1"]), B, H, W, C.c_ulonglong(seed),
+            _lib.ptr(st["kps"]), _lib.ptr(st["depth"]), _lib.ptr(st["scr"]), _lib.ptr(st["dsc"]), _lib.ptr(st["scores"]),
+            _lib.ptr(st["kp_scores"]), _lib.ptr(st["final_scores"]), _lib.ptr(st["pose"]), _lib.ptr(st["best_set"]),
+            _lib.ptr(st["inlier_mask"]), _lib.ptr(st["sampled_idx"]), _lib.ptr(st["status"]), _lib.ptr(ws), ws.numel(),
+            self._stream()), "mk_forward")
+
+    def forward(self, image0, image1, K0, K1, seed: int, use_graph: bool = True):
+        """Whole hot path (extract -> match -> solve) for a batch of pairs.  Returns the dict of STATIC output
+        tensors of this (B, H, W) geometry: they are overwritten by the next call with the same geometry."""
+        B = image0.shape[0]
+        H, W = PATCH * (image0.shape[-2] // PATCH), PATCH * (image0.shape[-1] // PATCH)
+        self._ws_for(B, H, W)
+        key = (B, H, W)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        if ent is None or ent["ws_ptr"] != self.ws.data_ptr():
+            ent = {"st": self._static_buffers(B, H, W), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(), "calls": 0}
+            self._graphs[key] = ent
+        st = ent["st"]
+        st["images"][:B].copy_(image0[..., :H, :W], non_blocking=True)
+        st["images"][B:].copy_(image1[..., :H, :W], non_blocking=True)
+        st["K0"].copy_(K0, non_blocking=True)
+        st["K1"].copy_(K1, non_blocking=True)
+        seed = (int(seed) & (2 ** 64 - 1)) or 1
+        if not use_graph:
+            self._call_forward(st, B, H, W, seed)
+            return st
+        if ent["graph"] is None:
+            # the first call runs eagerly (lazy one-time initialisation inside the library: function attributes,
+            # TMA descriptors), the second call is captured, later calls replay
+            if ent["calls"] == 0:
+                l0 = self.launch_count
+                self._call_forward(st, B, H, W, seed)
+                ent["launches"] = self.launch_count - l0
+                ent["calls"] = 1
+                return st
+            _lib.check(self.lib.mk_set_seed(self.h, C.c_ulonglong(seed), self._stream()), "mk_set_seed")
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._call_forward(st, B, H, W, 0)          # seed 0 = continue the device-side sequence
+            ent["graph"] = g
+            self.graph_replays = getattr(self, "graph_replays", 0)
+        _lib.check(self.lib.mk_set_seed(self.h, C.c_ulonglong(seed), self._stream()), "mk_set_seed")
+        ent["graph"].replay()
+        self.graph_replays += 1
+        self.graph_launches = getattr(self, "graph_launches", 0) + ent["launches"]
+        return st
 
     def solve(self, final_scores, kps, depth, K0, K1, seed: int, outer_idx=None, inner_idx=None, want_extras=False):
         """kps [2B,2,N], depth [2B,1,N] as produced by extract (image0 rows first)."""

@@ -65,7 +65,7 @@ class e2eProbabilisticProcrustesSolver:
         kps = torch.cat([batch["kps0"], batch["kps1"]], 0).detach().float().contiguous()
         depth = torch.cat([batch["depth_kp0"], batch["depth_kp1"]], 0).detach().float().contiguous()
         if seed is None:
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())     # follows torch.manual_seed like the reference
+            seed = int(torch.randint(1, 2 ** 62, (1,)).item())     # follows torch.manual_seed like the reference
         res = eng.solve(final, kps, depth, batch["K_color0"], batch["K_color1"], seed, outer_idx=outer_idx,
                         inner_idx=inner_idx, want_extras=True)
         pose = res["pose"]
@@ -135,7 +135,10 @@ class ComputeCorrespondences(nn.Module):
 class MickeyRelativePose(nn.Module):
     """Metric relative pose between two images (reference compute_pose.py:6-60)."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, dinov2_weights=None):
+        """dinov2_weights: optional DINOv2 state dict (native names: 'cls_token', 'blocks.0.attn.qkv.weight', ...)
+        or a path to one — the stand-in for the reference's download (mickey_extractor.py:15-17; there is no network
+        here).  Also read from $MICKEY_DINOV2_WEIGHTS.  Without it the backbone keeps seeded random-init values."""
         super().__init__()
         if cfg.MODEL is not None and cfg.MODEL != "MicKey":
             raise NotImplementedError()
@@ -148,6 +151,17 @@ class MickeyRelativePose(nn.Module):
         for name, t in synthetic_state_dict(cfg, seed=0).items():
             assert name.startswith("compute_matches.")
             self.compute_matches.__getattr__(name.split(".")[1]).add(".".join(name.split(".")[2:]), t)
+        import os
+        dinov2_weights = dinov2_weights or os.environ.get("MICKEY_DINOV2_WEIGHTS")
+        if dinov2_weights is not None:
+            if isinstance(dinov2_weights, str):
+                dinov2_weights = torch.load(dinov2_weights, map_location="cpu")
+            own = self.state_dict()
+            pre = "compute_matches.extractor.dinov2_vitl14."
+            missing = [k for k in own if k.startswith(pre) and k[len(pre):] not in dinov2_weights]
+            if missing:
+                raise KeyError(f"DINOv2 weights lack {missing[:3]} ...")
+            super().load_state_dict({**own, **{pre + k: v for k, v in dinov2_weights.items() if pre + k in own}})
         self.__dict__["_eng"] = None
         self.__dict__["_eng_version"] = -1
         self.__dict__["_param_version"] = 0
@@ -187,8 +201,61 @@ class MickeyRelativePose(nn.Module):
         return self._eng
 
     # -- the hot path ------------------------------------------------------------------------------------------
+    def _inlier_list(self, data, st, B, N):
+        """probabilisticProcrustes.py:305-327 from the kernel's winning set + hard-inlier mask (plumbing)."""
+        n_s = self.e2e_Procrustes.num_samples_matches
+        cells = st["sampled_idx"].long()[st["best_set"].long()]
+        mask = st["inlier_mask"] > 0.5
+        i0, i1 = torch.div(cells, N, rounding_mode="trunc"), cells % N
+        bidx = torch.arange(B, device=cells.device)[:, None].expand(-1, n_s)
+        w = data["final_scores"].reshape(B, N * N)[bidx, cells]
+        rows = torch.cat([data["kps0"][bidx, :, i0], data["kps1"][bidx, :, i1], w[..., None],
+                          data["depth_kp0"][bidx, :, i0], data["depth_kp1"][bidx, :, i1]], dim=-1)
+        if int(st["status"].item()) & 5:
+            return [torch.zeros([0, 5])] * B
+        out = []
+        for b in range(B):
+            rb = rows[b][mask[b]]
+            out.append(rb[torch.argsort(rb[:, 4], descending=True)])
+        return out
+
     @torch.no_grad()
     def forward(self, data, return_inliers=False):
+        """One C call (mk_forward) per batch, replayed from a CUDA graph after the first two calls.
+        `self.static_outputs = True` hands out the engine's static output buffers directly (they are overwritten
+        by the next forward of the same geometry); the default clones them so that every call returns fresh
+        tensors like the reference does."""
+        if getattr(self, "staged", False):
+            return self.forward_staged(data, return_inliers)
+        eng = self._engine()
+        im0, im1 = data["image0"], data["image1"]
+        B = im0.shape[0]
+        seed = int(torch.randint(1, 2 ** 62, (1,)).item())
+        st = eng.forward(im0.float(), im1.float(), data["K_color0"].float(), data["K_color1"].float(), seed,
+                         use_graph=getattr(self, "use_graph", True))
+        keep = (lambda t: t) if getattr(self, "static_outputs", False) else (lambda t: t.clone())
+        H, W = eng.geo
+        gh, gw = H // PATCH, W // PATCH
+        N = gh * gw
+        kps, depth, scr, dsc = keep(st["kps"]), keep(st["depth"]), keep(st["scr"]), keep(st["dsc"])
+        data["kps0_shape"], data["kps1_shape"], data["down_factor"] = [gh, gw], [gh, gw], self.compute_matches.down_factor
+        data["depth0_map"], data["depth1_map"] = depth[:B].reshape(B, 1, gh, gw), depth[B:].reshape(B, 1, gh, gw)
+        data["kps0"], data["kps1"] = kps[:B], kps[B:]
+        data["depth_kp0"], data["depth_kp1"] = depth[:B], depth[B:]
+        data["scr0"], data["scr1"] = scr[:B], scr[B:]
+        data["dsc0"], data["dsc1"] = dsc[:B], dsc[B:]
+        data["scores"], data["kp_scores"], data["final_scores"] = keep(st["scores"]), keep(st["kp_scores"]), keep(st["final_scores"])
+        pose = keep(st["pose"])
+        R, t, inliers = pose[:, :9].reshape(B, 3, 3), pose[:, 9:12].reshape(B, 1, 3), pose[:, 12:13]
+        if return_inliers:
+            data["inliers_list"] = self._inlier_list(data, st, B, N)
+        data["R"], data["t"], data["inliers"] = R, t, inliers
+        return R, t
+
+    @torch.no_grad()
+    def forward_staged(self, data, return_inliers=False):
+        """The same path as three C calls (mk_extract / mk_match / mk_solve_pose), mirroring the reference's
+        structure (compute_pose.py:20-37); used by the stage-wise tests."""
         self.compute_matches(data)
         # final_scores = scores * kp_scores (compute_pose.py:23) is produced by the matcher kernel's epilogue
         data["final_scores"] = data.pop("_final_scores_fused")
