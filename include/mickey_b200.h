@@ -132,7 +132,7 @@ typedef struct mk_gemm_args {
   int pad_h2, pad_w2, tok_per_img;
   float eps;
   int n_valid; float inv_temp;
-  const float* shift; const float* dustbin; float* row_sum;
+  const float* shift; const float* dustbin; float* row_sum;   /* LSE out: [groups, n_valid, 2*ceil(n_valid/128)] partial sums */
   const float* rs; const float* cs; const float* scr0; const float* scr1;
   float* scores; float* kp_scores; float* final_scores;
 } mk_gemm_args;
@@ -142,8 +142,11 @@ int mk_op_patch_gather(const float* img, void* patches_h, int n_img, int H, int 
                        const float* cls_pos, int D, void* stream);
 int mk_op_layernorm(const float* x, const float* w, const float* b, void* out_h, int rows, int D, float eps, int mode,
                     int gh, int gw, void* stream);
-int mk_op_attention(const void* qkv_h, void* out_h, int n_img, int T, int D, int heads, void* stream);
-int mk_op_linattn(const float* qkv_f, float* kv_f, void* msg_h, int n_img, int G, int h2, int w2, float eps, void* stream);
+/* impl: 0 = default (tcgen05), 1 = tcgen05/TMEM kernel, 2 = mma.sync kernel (cross-check) */
+int mk_op_attention(const void* qkv_h, void* out_h, int n_img, int T, int D, int heads, int impl, void* stream);
+/* kv_part_f: scratch [n_img, G, ceil(h2*w2/32), 8, 272] fp32 */
+int mk_op_linattn(const float* qkv_f, float* kv_part_f, float* kv_f, void* msg_h, int n_img, int G, int h2, int w2, float eps,
+                  void* stream);
 int mk_op_sample(const float* final_scores, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
                  long long ws_bytes, int* idx_out, int* status, void* stream);
 long long mk_op_sample_workspace_bytes(int B, int IM);

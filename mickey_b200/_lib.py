@@ -83,8 +83,8 @@ EXPORTS = {
                                      C.c_int, C.c_void_p]),
     "mk_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p]),
-    "mk_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "mk_op_linattn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "mk_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mk_op_linattn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "mk_op_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_void_p, C.c_longlong,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "mk_op_sample_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int]),

@@ -1,0 +1,286 @@
+// Fused multi-head attention on tcgen05 / TMEM / TMA (reference layers/attention.py:49-62).
+//
+//   out[img, q, head] = softmax(q k^T / 8) v          head_dim 64, T tokens per image (1939 at 720x540)
+//
+// CTA = 128 queries of one (image, head); KV is streamed in 128-key tiles.  192 threads:
+//   warps 0-3 : softmax + correction + epilogue; warp w owns TMEM lanes 32w..32w+31, thread == query row
+//   warp 4    : TMA producer (Q once; K and V rings, 2 stages each, 16 KB tiles, 128-byte swizzle)
+//   warp 5    : TMEM allocator + single-thread MMA issuer
+// TMEM (256 columns, two CTAs per SM):
+//   [0,128)   S = Q K^T, fp32             (tcgen05.mma SS, both operands K-major)
+//   [128,192) P = exp2(S - m), fp16 x2    (written by the softmax threads with tcgen05.st, read as the A operand)
+//   [192,256) O += P V, fp32              (tcgen05.mma TS, B = V tile as an MN-major operand)
+// Softmax is "online" with lazy rescaling: the running reference max m_ref only moves when the tile max exceeds
+// it by more than 8 (log2 units), so O in TMEM is rescaled rarely and P stays below 2^8 in fp16.  QK^T of tile
+// j+1 is issued as soon as the softmax warps have pulled S_j into registers, so it overlaps their exp work; the
+// second resident CTA fills the remaining bubbles.
+#include "gemm_tc.cuh"
+#include "ops.h"
+#include "gemm.h"
+#include <cstdlib>
+#include <cstring>
+
+namespace mk {
+
+constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64, FA_THREADS = 192, FA_KV_STAGES = 2;
+constexpr int FA_TILE_BYTES = 128 * 128;                                   // 128 rows x 64 fp16
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_KV_STAGES) + 1024 + 256;
+constexpr uint32_t FA_COL_S = 0, FA_COL_P = 128, FA_COL_O = 192, FA_TMEM_COLS = 256;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// MN-major operand (V tile: rows = keys (K dim), 64 contiguous fp16 of head_dim (N dim) per row, 128-byte swizzle):
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> 8-key groups 1024 bytes apart (SBO); n == 1.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO: stride between 64-element N blocks (single block here)
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: stride between groups of 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int D, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = base + FA_TILE_BYTES;
+  const uint32_t sV = sK + FA_KV_STAGES * FA_TILE_BYTES;
+  const uint32_t bars = sV + FA_KV_STAGES * FA_TILE_BYTES;
+  const uint32_t q_full = bars, k_full = bars + 8, k_empty = bars + 24, v_full = bars + 40, v_empty = bars + 56;
+  const uint32_t s_full = bars + 72, s_empty = bars + 80, p_full = bars + 88, pv_done = bars + 96, tmem_slot = bars + 104;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, im = blockIdx.z;
+  const int n_tiles = (T + FA_BK - 1) / FA_BK;
+  const int row_base = im * T;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_KV_STAGES; ++s) {
+      mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
+      mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
+    }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(FA_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      mbar_expect_tx(q_full, FA_TILE_BYTES);
+      tma_load_2d(sQ, &tmQKV, q_full, head * FA_D, row_base + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % FA_KV_STAGES;
+        const uint32_t par = ((j / FA_KV_STAGES) & 1) ^ 1;
+        mbar_wait(k_empty + 8 * st, par);
+        mbar_expect_tx(k_full + 8 * st, FA_TILE_BYTES);
+        tma_load_2d(sK + st * FA_TILE_BYTES, &tmQKV, k_full + 8 * st, D + head * FA_D, row_base + j * FA_BK);
+        mbar_wait(v_empty + 8 * st, par);
+        mbar_expect_tx(v_full + 8 * st, FA_TILE_BYTES);
+        tma_load_2d(sV + st * FA_TILE_BYTES, &tmQKV, v_full + 8 * st, 2 * D + head * FA_D, row_base + j * FA_BK);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FA_BK >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+    constexpr uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+    auto issue_qk = [&](int j) {
+      const int st = j % FA_KV_STAGES;
+      const uint64_t da = umma_desc_sw128(sQ), db = umma_desc_sw128(sK + st * FA_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < FA_D / UMMA_K; ++k)
+        umma_f16(tmem_base + FA_COL_S, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_qk, k > 0 ? 1u : 0u);
+      umma_commit(s_full);
+      umma_commit(k_empty + 8 * st);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(k_full, 0);
+    tc_fence_after();
+    if (elect_one()) issue_qk(0);
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) {
+        const int st1 = (j + 1) % FA_KV_STAGES;
+        mbar_wait(k_full + 8 * st1, ((j + 1) / FA_KV_STAGES) & 1);
+        mbar_wait(s_empty, j & 1);                 // softmax warps hold S_j in registers
+        tc_fence_after();
+        if (elect_one()) issue_qk(j + 1);
+        __syncwarp();
+      }
+      const int st = j % FA_KV_STAGES;
+      mbar_wait(v_full + 8 * st, (j / FA_KV_STAGES) & 1);
+      mbar_wait(p_full, j & 1);                    // P_j written (and O rescaled if needed)
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dv = umma_desc_mn_sw128(sV + st * FA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < FA_BK / UMMA_K; ++k)   // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
+          umma_f16_ts(tmem_base + FA_COL_O, tmem_base + FA_COL_P + k * 8, dv + (uint64_t)(k * 128), idesc_pv,
+                      (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(pv_done);
+        umma_commit(v_empty + 8 * st);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== softmax / correction / epilogue warps =====
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + FA_COL_S, tP = tmem_base + lane_off + FA_COL_P, tO = tmem_base + lane_off + FA_COL_O;
+    float m_ref = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float s[128];
+      {
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(tS + c * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = v[i];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);         // S buffer may be overwritten by QK^T of the next tile
+      const int valid = T - j * FA_BK;             // keys of this tile that exist (>= 1)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; ++i) {
+        s[i] = (i < valid) ? s[i] * scale_log2 : -INFINITY;
+        mx = fmaxf(mx, s[i]);
+      }
+      float alpha = 1.0f;
+      const bool move = (mx > m_ref + 8.0f);       // always true for j == 0 (m_ref = -inf)
+      if (move) { alpha = exp2f(m_ref - mx); m_ref = mx; }
+      float sum = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float p0 = exp2f(s[2 * i] - m_ref), p1 = exp2f(s[2 * i + 1] - m_ref);
+        sum += p0 + p1;
+        __half2 h = __floats2half2_rn(p0, p1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      l_run = l_run * alpha + sum;
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);           // P buffer free, O quiescent
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, move)) {       // rescale this warp's 32 rows of O (alpha == 1 where unchanged)
+          float o[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tO + c * 32, o);
+            uint32_t ob[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(o[i] * alpha);
+            tmem_st32(tO + c * 32, ob);
+          }
+        }
+      }
+      {
+        uint32_t half_pk[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) half_pk[i] = pk[c * 32 + i];
+          tmem_st32(tP + c * 32, half_pk);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> fp16
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + warp * 32 + lane;
+    const float inv = 1.0f / l_run;
+    __half* dst = out + ((long long)(row_base + q)) * D + head * FA_D;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float o[32];
+      tmem_ld32(tO + c * 32, o);
+      if (q < T) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= inv;
+        store_h32(dst + c * 32, o);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FA_TMEM_COLS) : "memory");
+  }
+}
+
+int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s) {
+  if (D != heads * FA_D) { set_last_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads); return MK_ERR_UNSUPPORTED; }
+  static bool attr = false;
+  if (!attr) {
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    attr = true;
+  }
+  CUtensorMap tm;
+  int rc = make_tensor_map_f16(&tm, qkv, (long long)n_img * T, 3LL * D, 3LL * D, FA_BQ);
+  if (rc) return rc;
+  dim3 grid(ceil_div(T, FA_BQ), heads, n_img);
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tm, (__half*)out, T, D, scale_log2);
+  MK_CUDA_CHECK(cudaGetLastError());
+  return MK_OK;
+}
+
+// impl: 0 = default (tcgen05 unless MICKEY_ATTN_IMPL=mma), 1 = tcgen05, 2 = mma.sync
+int attention_dispatch(const void* qkv, void* out, int n_img, int T, int D, int heads, int impl, cudaStream_t s) {
+  if (impl == 0) {
+    static int def = 0;
+    if (!def) { const char* e = getenv("MICKEY_ATTN_IMPL"); def = (e && strcmp(e, "mma") == 0) ? 2 : 1; }
+    impl = def;
+  }
+  return impl == 2 ? attention(qkv, out, n_img, T, D, heads, s) : attention_tc(qkv, out, n_img, T, D, heads, s);
+}
+
+}  // namespace mk

@@ -56,8 +56,9 @@ struct GemmParams {
   float inv_temp;
   const float* shift;       // [groups] softmax shift per pair
   const float* dustbin;     // device scalar or nullptr
-  float* row_sum;           // EPI_LSE out: [groups, n_valid]
-  const float* rs; const float* cs;     // EPI_DUAL in
+  float* row_sum;           // EPI_LSE out: partial sums [groups, n_valid, sum_slots] (slot = 2*n_tile + warp half)
+  int sum_slots;            // 2 * ceil(n_valid / 128)
+  const float* rs; const float* cs;     // EPI_DUAL in: the two partial-sum arrays (rows of S, rows of S^T)
   const float* scr0; const float* scr1; // [groups, n_valid]
   float* scores; float* kp_scores; float* final_scores;   // [groups, n_valid, n_valid]
 };

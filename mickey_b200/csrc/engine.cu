@@ -63,7 +63,7 @@ struct Workspace {
   __half* P; float* X; __half* XN; __half* QKV; __half* ATT; __half* H1;
   // heads
   __half* F; __half *T1, *S1, *O1, *T2, *S2, *O2, *T3, *S3, *CAT, *MSG, *HM, *T4k, *S4k, *T4d;
-  float *X32, *QKV32, *KV, *Y4k, *Y4d;
+  float *X32, *QKV32, *KV, *KVP, *Y4k, *Y4d;
   // head outputs kept for the matcher
   float* score_raw; __half* DSCX; float* nrm2; float* scr_copy;
   // matcher
@@ -92,13 +92,15 @@ Workspace carve(void* base, const mk_config& c, const Geo& g, int n_pairs) {
   w.T4k = cv.take<__half>(R * 3 * bd[3]); w.S4k = cv.take<__half>(R * 3 * bd[3]); w.T4d = cv.take<__half>(R * c.desc_dim);
   w.X32 = cv.take<float>(R * G * 128); w.QKV32 = cv.take<float>(R * G * 384);
   w.KV = cv.take<float>((size_t)g.n_img * G * 8 * 272);
+  w.KVP = cv.take<float>((size_t)g.n_img * G * linattn_kv_chunks(g.h2, g.w2) * 8 * 272);
   w.Y4k = cv.take<float>(R * 3 * bd[3]); w.Y4d = cv.take<float>(R * c.desc_dim);
   w.score_raw = cv.take<float>((size_t)g.n_img * g.N);
   w.DSCX = cv.take<__half>((size_t)g.n_img * g.N * 384);
   w.nrm2 = cv.take<float>((size_t)g.n_img * g.N);
   w.scr_copy = cv.take<float>((size_t)g.n_img * g.N);
   w.shift = cv.take<float>(n_pairs);
-  w.row_sum = cv.take<float>((size_t)n_pairs * g.N); w.col_sum = cv.take<float>((size_t)n_pairs * g.N);
+  const size_t slots = 2 * (size_t)ceil_div(g.N, 128);
+  w.row_sum = cv.take<float>((size_t)n_pairs * g.N * slots); w.col_sum = cv.take<float>((size_t)n_pairs * g.N * slots);
   const size_t streams = (size_t)n_pairs * c.it_matches;
   w.samp_ws = cv.take<uint8_t>(sampler_workspace_bytes(n_pairs, c.it_matches));
   w.idx = cv.take<int>(streams * c.num_sampled);
@@ -200,7 +202,7 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
     MK_KERNEL("vit.layernorm", layernorm(w.X, ln1w, ln1b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st));
     { GemmParams p = base_params(g.M, 3 * D, D); p.bias = bqkv; p.out_h = w.QKV; p.out_h_ld = 3 * D;
       MK_TRY(gemm(h, "vit.qkv", EPI_STORE_H, w.XN, g.M, D, wqkv, 3 * D, D, p, st)); }
-    MK_KERNEL("vit.attention", attention(w.QKV, w.ATT, g.n_img, g.T, D, c.heads, st));
+    MK_KERNEL("vit.attention", attention_dispatch(w.QKV, w.ATT, g.n_img, g.T, D, c.heads, 0, st));
     { GemmParams p = base_params(g.M, D, D); p.bias = bproj; p.gamma = ls1; p.out_f = w.X; p.out_f_ld = D;
       MK_TRY(gemm(h, "vit.proj", EPI_RESID_F, w.ATT, g.M, D, wproj, D, D, p, st)); }
     MK_KERNEL("vit.layernorm", layernorm(w.X, ln2w, ln2b, w.XN, (int)g.M, D, 1e-6f, 0, 0, 0, st));
@@ -267,7 +269,7 @@ int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, fl
     { GemmParams p = base_params(g.R, 384, 128); p.groups = G; p.a_col_group_off = 256; p.b_row_group_off = 384;
       p.out_f = w.QKV32; p.out_f_ld = G * 384; p.out_f_group_off = 384;
       MK_TRY(gemm(h, "head.att.qkv", EPI_STORE_F, w.CAT, g.R, G * 256, wqkv, G * 384, 128, p, st)); }
-    MK_KERNEL("head.att.kv", linattn_kv(w.QKV32, w.KV, g.n_img, G, g.h2, g.w2, st));
+    { ProfScope ps_(h, "head.att.kv", st); h->launches += 2; MK_TRY(linattn_kv(w.QKV32, w.KVP, w.KV, g.n_img, G, g.h2, g.w2, st)); }
     MK_KERNEL("head.att.msg", linattn_msg(w.QKV32, w.KV, w.MSG, g.n_img, G, g.h2, g.w2, 1e-6f, st));
     { GemmParams p = base_params(g.R, 128, 128); p.groups = G; p.a_col_group_off = 128; p.b_row_group_off = 128;
       p.gamma = n1w; p.beta = n1b; p.ln_group_off = 128; p.eps = 1e-5f;
@@ -339,14 +341,14 @@ int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores,
     return MK_ERR_UNSUPPORTED;
   }
   const float inv_t = 1.0f / c.temperature;
-  MK_KERNEL("match.prep", matcher_prep(w.nrm2, dust, inv_t, w.shift, w.row_sum, w.col_sum, n_pairs, N, st));
+  MK_KERNEL("match.prep", matcher_prep(w.nrm2, dust, inv_t, w.shift, n_pairs, N, st));
   const __half* A0 = w.DSCX;                                   // role-0 descriptors [n_pairs*N, 384]
   const __half* A1 = w.DSCX + (size_t)n_pairs * N * 384;       // role-1 descriptors
   const long long rows = (long long)n_pairs * N;
   auto mp = [&]() {
     GemmParams p = base_params(N, N, 384);
     p.groups = n_pairs; p.a_row_group_off = N; p.b_row_group_off = N; p.n_valid = N; p.inv_temp = inv_t;
-    p.shift = w.shift; p.dustbin = dust;
+    p.shift = w.shift; p.dustbin = dust; p.sum_slots = 2 * ceil_div(N, 128);
     return p;
   };
   { GemmParams p = mp(); p.row_sum = w.row_sum; MK_TRY(gemm(h, "match.lse", EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
@@ -583,6 +585,7 @@ int mk_op_gemm(const mk_gemm_args* a, void* stream) {
   p.res_h = (const __half*)a->res_h; p.res_h_ld = a->res_h_ld; p.res_h_group_off = a->res_h_group_off;
   p.aux = a->aux; p.aux_group_mask = a->aux_group_mask; p.pad_h2 = a->pad_h2; p.pad_w2 = a->pad_w2; p.tok_per_img = a->tok_per_img;
   p.eps = a->eps; p.n_valid = a->n_valid; p.inv_temp = a->inv_temp; p.shift = a->shift; p.dustbin = a->dustbin;
+  p.sum_slots = 2 * ceil_div(a->n_valid > 0 ? a->n_valid : 1, 128);
   p.row_sum = a->row_sum; p.rs = a->rs; p.cs = a->cs; p.scr0 = a->scr0; p.scr1 = a->scr1;
   p.scores = a->scores; p.kp_scores = a->kp_scores; p.final_scores = a->final_scores;
   GemmOperand A{a->a, a->a_rows, a->a_cols, a->a_ld}, B{a->b, a->b_rows, a->b_cols, a->b_ld};
@@ -597,11 +600,12 @@ int mk_op_layernorm(const float* x, const float* w, const float* b, void* out, i
                     int gh, int gw, void* stream) {
   return layernorm(x, w, b, out, rows, D, eps, mode, gh, gw, (cudaStream_t)stream);
 }
-int mk_op_attention(const void* qkv, void* out, int n_img, int T, int D, int heads, void* stream) {
-  return attention(qkv, out, n_img, T, D, heads, (cudaStream_t)stream);
+int mk_op_attention(const void* qkv, void* out, int n_img, int T, int D, int heads, int impl, void* stream) {
+  return attention_dispatch(qkv, out, n_img, T, D, heads, impl, (cudaStream_t)stream);
 }
-int mk_op_linattn(const float* qkv, float* kv, void* msg, int n_img, int Gn, int h2, int w2, float eps, void* stream) {
-  MK_TRY(linattn_kv(qkv, kv, n_img, Gn, h2, w2, (cudaStream_t)stream));
+int mk_op_linattn(const float* qkv, float* kv_part, float* kv, void* msg, int n_img, int Gn, int h2, int w2, float eps,
+                  void* stream) {
+  MK_TRY(linattn_kv(qkv, kv_part, kv, n_img, Gn, h2, w2, (cudaStream_t)stream));
   return linattn_msg(qkv, kv, msg, n_img, Gn, h2, w2, eps, (cudaStream_t)stream);
 }
 long long mk_op_sample_workspace_bytes(int B, int IM) { return (long long)sampler_workspace_bytes(B, IM) + 512; }

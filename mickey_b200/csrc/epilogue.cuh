@@ -164,7 +164,12 @@ __device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int
   const size_t gv = (size_t)g * p.n_valid;
   const int my_row = row0 + lane;
   const bool row_ok = my_row < p.n_valid;
-  const float inv_r = row_ok ? 1.0f / (__ldg(p.rs + gv + my_row) + dust) : 0.0f;
+  float rsum = 0.f, csum = 0.f;
+  if (row_ok) {
+    const float* rp = p.rs + (gv + my_row) * p.sum_slots;
+    for (int k = 0; k < p.sum_slots; ++k) rsum += __ldg(rp + k);      // fixed order: bit-reproducible
+  }
+  const float inv_r = row_ok ? 1.0f / (rsum + dust) : 0.0f;
   const float s0 = row_ok ? __ldg(p.scr0 + gv + my_row) : 0.0f;
   const float k2 = p.inv_temp * L2E;
 #pragma unroll
@@ -175,7 +180,11 @@ __device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int
   __syncwarp();
   const int col = n0 + lane;
   const bool col_ok = col < p.n_valid;
-  const float inv_c = col_ok ? 1.0f / (__ldg(p.cs + gv + col) + dust) : 0.0f;
+  if (col_ok) {
+    const float* cp = p.cs + (gv + col) * p.sum_slots;
+    for (int k = 0; k < p.sum_slots; ++k) csum += __ldg(cp + k);
+  }
+  const float inv_c = col_ok ? 1.0f / (csum + dust) : 0.0f;
   const float s1 = col_ok ? __ldg(p.scr1 + gv + col) : 0.0f;
   const int rows = min(32, p.n_valid - row0);
 #pragma unroll 4

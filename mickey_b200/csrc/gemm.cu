@@ -138,7 +138,10 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
       for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
       s += lse_partial(p, g, n0 + c * 32, v);
     }
-    if (m < p.n_valid) atomicAdd(p.row_sum + (size_t)g * p.n_valid + m, s);
+    if (m < p.n_valid) {
+      float* slot = p.row_sum + ((size_t)g * p.n_valid + m) * p.sum_slots + blockIdx.y * 2;
+      slot[0] = s; slot[1] = 0.f;
+    }
   } else if constexpr (EPI == EPI_DUAL) {
     float* stage = reinterpret_cast<float*>(&As[0][0]) + (t >> 5) * (32 * 33);   // tiles are idle now
     for (int c = 0; c < BN / 32; ++c) {

@@ -253,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(taddr + c * 32, v);
         s += lse_partial(p, g, n0 + c * 32, v);
       }
-      if (m < p.n_valid) atomicAdd(p.row_sum + (size_t)g * p.n_valid + m, s);
+      if (m < p.n_valid) p.row_sum[((size_t)g * p.n_valid + m) * p.sum_slots + blockIdx.y * 2 + half] = s;
     } else if constexpr (EPI == EPI_DUAL) {
       // per-warp 32x33 fp32 staging tile in the (now idle) pipeline smem: transposes "thread == row" into
       // "lane == column" so that every store instruction writes one contiguous 128-byte row segment

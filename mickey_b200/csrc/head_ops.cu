@@ -17,8 +17,9 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v + 1.0f : exp
 // ------------------------------------------------------------------------------------------------------
 // Linear attention, reduction half (reference att_layers/attention.py:55-61):
 //   K = elu(k)+1;  KV[h] = sum_s K[s,h,:]^T (v[s,h,:] / L);  Ksum[h] = sum_s K[s,h,:]
-// qkv fp32 [R, G*384] (q|k|v per group, 8 heads x 16).  out fp32 [n_img, G, 8, 272] (256 KV + 16 Ksum),
-// zeroed by the launcher and accumulated with atomics.
+// qkv fp32 [R, G*384] (q|k|v per group, 8 heads x 16).  Each CTA writes the partial sums of its 32-row chunk to
+// part[n_img, G, chunk, 8, 272]; linattn_kv_reduce_kernel adds the chunks in a fixed order (bit-reproducible,
+// no float atomics) into out fp32 [n_img, G, 8, 272] (256 KV + 16 Ksum).
 // grid (row chunks of 32, G, n_img), 256 threads: thread t owns head h = t/32, key dim d = (t%32)/2 and eight
 // value dims; the chunk's k and v rows of all 8 heads are staged in shared memory once.
 // ------------------------------------------------------------------------------------------------------
@@ -59,10 +60,23 @@ linattn_kv_kernel(const float* __restrict__ qkv, float* __restrict__ kvout, int 
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = fmaf(kk, Vs[r][head * 16 + vh + j], acc[j]);
   }
-  float* o = kvout + (((long long)im * G + g) * 8 + head) * 272;
+  float* o = kvout + ((((long long)im * G + g) * gridDim.x + blockIdx.x) * 8 + head) * 272;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(o + d * 16 + vh + j, acc[j]);
-  if (vh == 0) atomicAdd(o + 256 + d, ksum);
+  for (int j = 0; j < 8; ++j) o[d * 16 + vh + j] = acc[j];
+  if (vh == 0) o[256 + d] = ksum;
+}
+
+// out[i] = sum_c part[c][i] over the row chunks, one thread per output element.  grid (G, n_img).
+__global__ void __launch_bounds__(256)
+linattn_kv_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int G, int chunks) {
+  const int g = blockIdx.x, im = blockIdx.y;
+  const float* src = part + ((long long)im * G + g) * chunks * (8 * 272);
+  float* dst = out + ((long long)im * G + g) * (8 * 272);
+  for (int i = threadIdx.x; i < 8 * 272; i += 256) {
+    float a = 0.f;
+    for (int c = 0; c < chunks; ++c) a += src[(long long)c * (8 * 272) + i];
+    dst[i] = a;
+  }
 }
 
 // Linear attention, query half (attention.py:52,60-61): msg = (Q KV) / (Q . Ksum + eps) * L, Q = elu(q)+1.
@@ -110,9 +124,13 @@ linattn_msg_kernel(const float* __restrict__ qkv, const float* __restrict__ kv, 
   reinterpret_cast<uint4*>(dst)[1] = u1;
 }
 
-int linattn_kv(const float* qkv, float* kv, int n_img, int G, int h2, int w2, cudaStream_t s) {
-  MK_CUDA_CHECK(cudaMemsetAsync(kv, 0, (size_t)n_img * G * 8 * 272 * sizeof(float), s));
-  linattn_kv_kernel<<<dim3(ceil_div(h2 * w2, KV_ROWS), G, n_img), 256, 0, s>>>(qkv, kv, G, h2, w2);
+int linattn_kv_chunks(int h2, int w2) { return ceil_div(h2 * w2, KV_ROWS); }
+
+int linattn_kv(const float* qkv, float* kv_part, float* kv, int n_img, int G, int h2, int w2, cudaStream_t s) {
+  const int chunks = linattn_kv_chunks(h2, w2);
+  linattn_kv_kernel<<<dim3(chunks, G, n_img), 256, 0, s>>>(qkv, kv_part, G, h2, w2);
+  MK_CUDA_CHECK(cudaGetLastError());
+  linattn_kv_reduce_kernel<<<dim3(G, n_img), 256, 0, s>>>(kv_part, kv, G, chunks);
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
@@ -266,18 +284,16 @@ int desc_out(const float* y, float* dsc_cm, void* dsc_x, float* nrm2, int n_img,
 
 // Softmax shift per pair (an upper bound of every logit so that exp never overflows):
 //   shift[b] = max( max_i|d0_i| * max_j|d1_j| / T , dustbin )        (Cauchy-Schwarz)
-// Also zeroes the row/col sum accumulators of the pair.  One block per pair.
+// One block per pair.
 __global__ void __launch_bounds__(256)
 matcher_prep_kernel(const float* __restrict__ nrm2, const float* __restrict__ dustbin, float inv_temp,
-                    float* __restrict__ shift, float* __restrict__ row_sum, float* __restrict__ col_sum, int B, int N) {
+                    float* __restrict__ shift, int B, int N) {
   __shared__ float r0[256], r1[256];
   const int b = blockIdx.x, t = threadIdx.x;
   float m0 = 0.f, m1 = 0.f;
   for (int n = t; n < N; n += 256) {
     m0 = fmaxf(m0, nrm2[(long long)b * N + n]);
     m1 = fmaxf(m1, nrm2[(long long)(B + b) * N + n]);
-    row_sum[(long long)b * N + n] = 0.f;
-    col_sum[(long long)b * N + n] = 0.f;
   }
   r0[t] = m0; r1[t] = m1;
   __syncthreads();
@@ -292,9 +308,8 @@ matcher_prep_kernel(const float* __restrict__ nrm2, const float* __restrict__ du
   }
 }
 
-int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float* shift, float* row_sum, float* col_sum,
-                 int B, int N, cudaStream_t s) {
-  matcher_prep_kernel<<<B, 256, 0, s>>>(nrm2, dustbin, inv_temp, shift, row_sum, col_sum, B, N);
+int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float* shift, int B, int N, cudaStream_t s) {
+  matcher_prep_kernel<<<B, 256, 0, s>>>(nrm2, dustbin, inv_temp, shift, B, N);
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }

@@ -7,17 +7,19 @@ namespace mk {
 // vit_ops.cu
 int patch_gather(const float* img, void* P, int n_img, int H, int W, int kpad, float* X, const float* cls_pos, int D, cudaStream_t s);
 int layernorm(const float* x, const float* w, const float* b, void* out, int rows, int D, float eps, int mode, int gh, int gw, cudaStream_t s);
-int attention(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s);
+int attention(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s);      // mma.sync version (v1, kept as a cross-check)
+int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s);   // tcgen05 / TMEM version
+int attention_dispatch(const void* qkv, void* out, int n_img, int T, int D, int heads, int impl, cudaStream_t s);
 
 // head_ops.cu
-int linattn_kv(const float* qkv, float* kv, int n_img, int G, int h2, int w2, cudaStream_t s);
+int linattn_kv_chunks(int h2, int w2);
+int linattn_kv(const float* qkv, float* kv_part, float* kv, int n_img, int G, int h2, int w2, cudaStream_t s);
 int linattn_msg(const float* qkv, const float* kv, void* msg, int n_img, int G, int h2, int w2, float eps, cudaStream_t s);
 int kp_head_out(const float* y, const float* w_depth, const float* w_xy, const float* w_score, float* depth, float* kps,
                 float* score_raw, float* scr, int n_img, int gh, int gw, int depth_sigmoid, float max_depth,
                 float down_factor, int use_softmax, cudaStream_t s);
 int desc_out(const float* y, float* dsc_cm, void* dsc_x, float* nrm2, int n_img, int gh, int gw, int normalize, cudaStream_t s);
-int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float* shift, float* row_sum, float* col_sum,
-                 int B, int N, cudaStream_t s);
+int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float* shift, int B, int N, cudaStream_t s);
 
 // ransac.cu
 struct RansacParams {

@@ -131,13 +131,15 @@ def test_layernorm_scatter_to_padded_grid():
     assert float(out[:, 0].abs().max()) == 0 and float(out[:, :, 0].abs().max()) == 0
 
 
-@pytest.mark.parametrize("T,heads", [(211, 6), (1939, 6), (64, 12)])
-def test_attention(T, heads):
+@pytest.mark.parametrize("impl", [2, 1], ids=["mma", "tcgen05"])
+@pytest.mark.parametrize("T,heads,scale", [(211, 6, 1.5), (1939, 6, 1.5), (64, 12, 1.5), (300, 6, 6.0)])
+def test_attention(T, heads, scale, impl):
+    """scale 6.0 makes the logits span > 2^8 so that the lazy O-rescaling path of the tcgen05 kernel is exercised."""
     lib = _lib.load()
     n_img, D = 2, heads * 64
-    qkv = (_rand(n_img * T, 3 * D, seed=26) * 1.5).half()
+    qkv = (_rand(n_img * T, 3 * D, seed=26) * scale).half()
     out = torch.zeros(n_img * T, D, dtype=torch.float16, device=DEV)
-    _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), n_img, T, D, heads, stream()))
+    _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), n_img, T, D, heads, impl, stream()))
     q, k, v = qkv.float().reshape(n_img, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(n_img * T, D)
     assert rel_err(out, ref) < 2e-3
@@ -169,8 +171,9 @@ def test_linear_attention():
     R = n_img * h2 * w2
     qkv = _rand(R, G * 384, seed=30)
     kv = torch.zeros(n_img, G, 8, 272, device=DEV)
+    kvp = torch.zeros(n_img, G, (h2 * w2 + 31) // 32, 8, 272, device=DEV)
     msg = torch.zeros(R, G * 128, dtype=torch.float16, device=DEV)
-    _lib.check(lib.mk_op_linattn(_lib.ptr(qkv), _lib.ptr(kv), _lib.ptr(msg), n_img, G, h2, w2, 1e-6, stream()))
+    _lib.check(lib.mk_op_linattn(_lib.ptr(qkv), _lib.ptr(kvp), _lib.ptr(kv), _lib.ptr(msg), n_img, G, h2, w2, 1e-6, stream()))
     t = qkv.reshape(n_img, h2, w2, G, 3, 8, 16)[:, 1:-1, 1:-1].reshape(n_img, gh * gw, G, 3, 8, 16)
     for g in range(G):
         q, k, v = t[:, :, g, 0], t[:, :, g, 1], t[:, :, g, 2]
@@ -199,7 +202,8 @@ def test_matcher_epilogues_vs_dual_softmax(impl):
 
     a0, a1 = split(d0, 0), split(d1, 1)
     shift = torch.full((B,), 10.0, device=DEV)
-    rs, cs = torch.zeros(B, N, device=DEV), torch.zeros(B, N, device=DEV)
+    slots = 2 * ((N + 127) // 128)
+    rs, cs = torch.zeros(B, N, slots, device=DEV), torch.zeros(B, N, slots, device=DEV)
     common = dict(groups=B, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=1 / T, shift=shift, dustbin=dust)
     gemm("LSE", a0, a1, N, N, 384, impl=impl, row_sum=rs, **common)
     gemm("LSE", a1, a0, N, N, 384, impl=impl, row_sum=cs, **common)

@@ -9,8 +9,8 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mickey_b200.config import mickey_cfg, VARIANTS  # noqa: E402
-from mickey_b200.model import build_model  # noqa: E402
-from mickey_b200.weights import synthetic_checkpoint, synthetic_state_dict  # noqa: E402
+from mickey_b200.model import MickeyRelativePose  # noqa: E402
+from mickey_b200.weights import synthetic_state_dict  # noqa: E402
 from oracle import mickey_oracle as mo  # noqa: E402
 from tests.common import synthetic_pair, rel_err  # noqa: E402
 
@@ -18,7 +18,9 @@ variant = sys.argv[1] if len(sys.argv) > 1 else "vitb"
 H = int(sys.argv[2]) if len(sys.argv) > 3 else 224
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 182
 cfg = mickey_cfg(variant, 2, 8)
-model = build_model(cfg, synthetic_checkpoint(cfg, seed=1, with_backbone=True))
+model = MickeyRelativePose(cfg)
+model.load_state_dict(synthetic_state_dict(cfg, seed=1))
+model = model.cuda().eval()
 sd = synthetic_state_dict(mickey_cfg(variant, 2, 8, float16=False), seed=1)
 data = synthetic_pair(1, H, W, seed=6)
 gdata = {k: v.cuda() for k, v in data.items()}

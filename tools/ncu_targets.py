@@ -32,7 +32,7 @@ if "attention" in which:
     qkv = torch.randn(2 * T, 3 * D, device=dev).half()
     out = torch.empty(2 * T, D, dtype=torch.float16, device=dev)
     for _ in range(reps):
-        _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), 2, T, D, 6, stream()))
+        _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), 2, T, D, 6, 0, stream()))
 if "conv" in which:         # heads resblock1 conv2: 4 groups x (512 -> 512, 3x3) over 2 padded 53x40 images
     h2, w2, G, Cc = 53, 40, 4, 512
     R = 2 * h2 * w2
@@ -53,13 +53,13 @@ if "dual" in which:
         return torch.cat([hi, lo, hi] if role == 0 else [hi, hi, lo], dim=-1).reshape(N, 384).contiguous()
     a0, a1 = split(d0, 0), split(d1, 1)
     shift, dust = torch.full((1,), 10.0, device=dev), torch.ones(1, device=dev)
-    rs, cs = torch.zeros(1, N, device=dev), torch.zeros(1, N, device=dev)
+    rs, cs = torch.zeros(1, N, 32, device=dev), torch.ones(1, N, 32, device=dev)
     s0, s1 = torch.rand(1, N, device=dev), torch.rand(1, N, device=dev)
     sc, kp, fin = (torch.empty(1, N, N, device=dev) for _ in range(3))
     common = dict(groups=1, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, shift=shift, dustbin=dust)
     for _ in range(reps):
         gemm("LSE", a0, a1, N, N, 384, row_sum=rs, **common)
-        gemm("DUAL", a0, a1, N, N, 384, rs=rs, cs=cs + 1, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
+        gemm("DUAL", a0, a1, N, N, 384, rs=rs, cs=cs, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
 if "sampler" in which:
     p = torch.rand(1, N * N, device=dev) * 1e-9
     nb = lib.mk_op_sample_workspace_bytes(1, 8)
@@ -72,8 +72,9 @@ if "linattn" in which:
     h2, w2, G = 53, 40, 4
     qkv = torch.randn(2 * h2 * w2, G * 384, device=dev)
     kv = torch.zeros(2, G, 8, 272, device=dev)
+    kvp = torch.zeros(2, G, (h2 * w2 + 31) // 32, 8, 272, device=dev)
     msg = torch.zeros(2 * h2 * w2, G * 128, dtype=torch.float16, device=dev)
     for _ in range(reps):
-        _lib.check(lib.mk_op_linattn(_lib.ptr(qkv), _lib.ptr(kv), _lib.ptr(msg), 2, G, h2, w2, 1e-6, stream()))
+        _lib.check(lib.mk_op_linattn(_lib.ptr(qkv), _lib.ptr(kvp), _lib.ptr(kv), _lib.ptr(msg), 2, G, h2, w2, 1e-6, stream()))
 torch.cuda.synchronize()
 print("done", sorted(which))
