@@ -152,25 +152,31 @@ __device__ __forceinline__ float lse_partial(const GemmParams& p, int g, int n0,
   return s;
 }
 
-// EPI_DUAL, coalesced: the warp owns rows row0..row0+31 (lane == row on entry) and columns n0..n0+31.
-// Each lane scales its row by the row statistics, the 32x32 block is transposed through `stage`
-// ([32][33] floats, warp-private), then lane == column applies the column statistics and every store
-// instruction writes one contiguous 128-byte segment of a row of scores / kp_scores / final_scores.
-__device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int row0, int lane, int n0,
-                                                 const float (&v)[32], float* stage) {
-  const float L2E = 1.4426950408889634f;
-  const float sh = __ldg(p.shift + g) * L2E;
-  const float dust = p.dustbin ? exp2f(__ldg(p.dustbin) * L2E - sh) : 0.0f;
-  const size_t gv = (size_t)g * p.n_valid;
-  const int my_row = row0 + lane;
-  const bool row_ok = my_row < p.n_valid;
-  float rsum = 0.f, csum = 0.f;
-  if (row_ok) {
-    const float* rp = p.rs + (gv + my_row) * p.sum_slots;
-    for (int k = 0; k < p.sum_slots; ++k) rsum += __ldg(rp + k);      // fixed order: bit-reproducible
+// Sum of the partial-sum slots of one row, in a fixed order (bit-reproducible), with independent 16-byte loads.
+__device__ __forceinline__ float sum_slots(const float* __restrict__ ptr, int n) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  if ((n & 3) == 0) {
+    for (; k < n; k += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ptr + k));
+      a0 += t.x; a1 += t.y; a2 += t.z; a3 += t.w;
+    }
+  } else {
+    for (; k < n; ++k) a0 += __ldg(ptr + k);
   }
-  const float inv_r = row_ok ? 1.0f / (rsum + dust) : 0.0f;
-  const float s0 = row_ok ? __ldg(p.scr0 + gv + my_row) : 0.0f;
+  return (a0 + a1) + (a2 + a3);
+}
+
+// EPI_DUAL, coalesced: the warp owns rows row0..row0+31 (lane == row on entry) and columns n0..n0+31.
+// Each lane scales its row by the row statistics (inv_r, s0: computed once per tile by the caller), the 32x32
+// block is transposed through `stage` ([32][33] floats, warp-private), then lane == column applies the column
+// statistics and every store instruction writes one contiguous 128-byte segment of a row of
+// scores / kp_scores / final_scores.
+__device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int row0, int lane, int n0,
+                                                 const float (&v)[32], float* stage, float inv_r, float s0,
+                                                 float sh, float dust) {
+  const float L2E = 1.4426950408889634f;
+  const size_t gv = (size_t)g * p.n_valid;
   const float k2 = p.inv_temp * L2E;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -180,11 +186,7 @@ __device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int
   __syncwarp();
   const int col = n0 + lane;
   const bool col_ok = col < p.n_valid;
-  if (col_ok) {
-    const float* cp = p.cs + (gv + col) * p.sum_slots;
-    for (int k = 0; k < p.sum_slots; ++k) csum += __ldg(cp + k);
-  }
-  const float inv_c = col_ok ? 1.0f / (csum + dust) : 0.0f;
+  const float inv_c = col_ok ? 1.0f / (sum_slots(p.cs + (gv + col) * p.sum_slots, p.sum_slots) + dust) : 0.0f;
   const float s1 = col_ok ? __ldg(p.scr1 + gv + col) : 0.0f;
   const int rows = min(32, p.n_valid - row0);
 #pragma unroll 4
@@ -199,6 +201,18 @@ __device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int
     }
   }
   __syncwarp();
+}
+
+// per-row quantities of the dual-softmax epilogue for row `my_row` of pair g
+__device__ __forceinline__ void dual_row_setup(const GemmParams& p, int g, int my_row, float& inv_r, float& s0,
+                                               float& sh, float& dust) {
+  const float L2E = 1.4426950408889634f;
+  sh = __ldg(p.shift + g) * L2E;
+  dust = p.dustbin ? exp2f(__ldg(p.dustbin) * L2E - sh) : 0.0f;
+  const size_t gv = (size_t)g * p.n_valid;
+  const bool row_ok = my_row < p.n_valid;
+  inv_r = row_ok ? 1.0f / (sum_slots(p.rs + (gv + my_row) * p.sum_slots, p.sum_slots) + dust) : 0.0f;
+  s0 = row_ok ? __ldg(p.scr0 + gv + my_row) : 0.0f;
 }
 
 // EPI_LN: normalise the 128-wide row (N == 128 == tile width), then optional residual add.

@@ -144,10 +144,12 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
     }
   } else if constexpr (EPI == EPI_DUAL) {
     float* stage = reinterpret_cast<float*>(&As[0][0]) + (t >> 5) * (32 * 33);   // tiles are idle now
+    float inv_r, s0, sh, dust;
+    dual_row_setup(p, g, m, inv_r, s0, sh, dust);
     for (int c = 0; c < BN / 32; ++c) {
       if (n0 + c * 32 < p.n_valid) {
         for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
-        dual_store_chunk(p, g, m0 + (t >> 5) * 32, t & 31, n0 + c * 32, v, stage);
+        dual_store_chunk(p, g, m0 + (t >> 5) * 32, t & 31, n0 + c * 32, v, stage, inv_r, s0, sh, dust);
       }
     }
   } else {

@@ -258,10 +258,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // per-warp 32x33 fp32 staging tile in the (now idle) pipeline smem: transposes "thread == row" into
       // "lane == column" so that every store instruction writes one contiguous 128-byte row segment
       float* stage = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * 33);
+      float inv_r, s0, sh, dust;
+      dual_row_setup(p, g, m, inv_r, s0, sh, dust);
       for (int c = c_begin; c < c_end; ++c) {
         if (n0 + c * 32 < p.n_valid) {
           tmem_ld32(taddr + c * 32, v);
-          dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage);
+          dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage, inv_r, s0, sh, dust);
         }
       }
     } else {

@@ -293,16 +293,11 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # -- stages ------------------------------------------------------------------------------------------------
-    def crop(self, images: torch.Tensor) -> torch.Tensor:
-        H, W = images.shape[-2:]
-        Hc, Wc = PATCH * (H // PATCH), PATCH * (W // PATCH)
-        if (Hc, Wc) != (H, W):
-            images = images[..., :Hc, :Wc]
-        return images.contiguous()
-
     def extract(self, images: torch.Tensor):
-        """images fp32 [2B, 3, H, W] (image0 batch then image1 batch) -> kps, depth, scr, dsc."""
-        images = self.crop(images.float())
+        """images fp32 [2B, 3, H, W] (image0 batch then image1 batch) -> kps, depth, scr, dsc.
+        H, W need not be multiples of 14: the patch gather reads only the top-left 14*(H//14) x 14*(W//14) crop
+        (reference mickey_extractor.py:46), so no cropped copy is made."""
+        images = images.float().contiguous()
         n_img, _, H, W = images.shape
         assert n_img % 2 == 0
         B, N = n_img // 2, (H // PATCH) * (W // PATCH)
@@ -352,7 +347,7 @@ class Engine:
         """Whole hot path (extract -> match -> solve) for a batch of pairs.  Returns the dict of STATIC output
         tensors of this (B, H, W) geometry: they are overwritten by the next call with the same geometry."""
         B = image0.shape[0]
-        H, W = PATCH * (image0.shape[-2] // PATCH), PATCH * (image0.shape[-1] // PATCH)
+        H, W = image0.shape[-2], image0.shape[-1]
         self._ws_for(B, H, W)
         key = (B, H, W)
         if not hasattr(self, "_graphs"):
@@ -362,8 +357,8 @@ class Engine:
             ent = {"st": self._static_buffers(B, H, W), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(), "calls": 0}
             self._graphs[key] = ent
         st = ent["st"]
-        st["images"][:B].copy_(image0[..., :H, :W], non_blocking=True)
-        st["images"][B:].copy_(image1[..., :H, :W], non_blocking=True)
+        st["images"][:B].copy_(image0, non_blocking=True)      # H2D straight from (pinned) host memory, or D2D
+        st["images"][B:].copy_(image1, non_blocking=True)
         st["K0"].copy_(K0, non_blocking=True)
         st["K1"].copy_(K1, non_blocking=True)
         seed = (int(seed) & (2 ** 64 - 1)) or 1

@@ -110,8 +110,7 @@ def test_solver_with_injected_reference_draws(name):
     spec, gold, cfg, data = _oracle_inputs(name)
     _, model = _model(spec["variant"], spec["it_matches"], spec["it_ransac"], spec["weight_seed"])
     eng = model._engine()
-    H, W = 14 * (spec["height"] // 14), 14 * (spec["width"] // 14)
-    eng._ws_for(spec["batch"], H, W)
+    eng._ws_for(spec["batch"], spec["height"], spec["width"])
     trace = {}
     mo.solve_pose(data["final_scores"], data["kps0"], data["depth_kp0"], data["kps1"], data["depth_kp1"],
                   data["K_color0"], data["K_color1"], cfg, outer_idx=gold["outer_idx"].long(),
