@@ -41,6 +41,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -83,6 +88,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
   const int n_tiles = (T + FA_BK - 1) / FA_BK;
   const int row_base = im * T;
 
+  pdl_trigger();
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
     mbar_init(q_full, 1);
@@ -101,6 +107,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();
 
   if (warp == 4) {
     // ===== TMA producer =====
@@ -182,24 +189,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);         // S buffer may be overwritten by QK^T of the next tile
       const int valid = T - j * FA_BK;             // keys of this tile that exist (>= 1)
-      float mx = -INFINITY;
+      if (valid < FA_BK) {                         // only the last tile has a key tail (warp-uniform branch)
 #pragma unroll
-      for (int i = 0; i < 128; ++i) {
-        s[i] = (i < valid) ? s[i] * scale_log2 : -INFINITY;
-        mx = fmaxf(mx, s[i]);
+        for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : -INFINITY;
       }
+      float mx = -INFINITY;                        // max of the RAW logits; scale_log2 > 0 commutes with max
+#pragma unroll
+      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, s[i]);
+      mx *= scale_log2;
       float alpha = 1.0f;
       const bool move = (mx > m_ref + 8.0f);       // always true for j == 0 (m_ref = -inf)
-      if (move) { alpha = exp2f(m_ref - mx); m_ref = mx; }
-      float sum = 0.f;
+      if (move) { alpha = ex2_approx(m_ref - mx); m_ref = mx; }
+      // p = 2^(s*scale - m_ref): one FFMA + one MUFU.EX2 per element, two partial sums for ILP
+      float sum0 = 0.f, sum1 = 0.f;
+      const float neg_m = -m_ref;
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        const float p0 = exp2f(s[2 * i] - m_ref), p1 = exp2f(s[2 * i + 1] - m_ref);
-        sum += p0 + p1;
+        const float p0 = ex2_approx(fmaf(s[2 * i], scale_log2, neg_m)), p1 = ex2_approx(fmaf(s[2 * i + 1], scale_log2, neg_m));
+        sum0 += p0; sum1 += p1;
         __half2 h = __floats2half2_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&h);
       }
+      const float sum = sum0 + sum1;
       l_run = l_run * alpha + sum;
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);           // P buffer free, O quiescent
@@ -268,8 +280,7 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   if (rc) return rc;
   dim3 grid(ceil_div(T, FA_BQ), heads, n_img);
   const float scale_log2 = 0.125f * 1.4426950408889634f;
-  attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(tm, (__half*)out, T, D, scale_log2);
-  MK_CUDA_CHECK(cudaGetLastError());
+  MK_CUDA_CHECK(launch_k(attention_tc_kernel, grid, dim3(FA_THREADS), (size_t)FA_SMEM, s, tm, (__half*)out, T, D, scale_log2));
   return MK_OK;
 }
 

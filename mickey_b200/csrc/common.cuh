@@ -65,6 +65,31 @@ struct GemmParams {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every kernel of the pipeline is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it lets the
+// NEXT kernel's CTAs be scheduled as soon as this grid has issued pdl_trigger() and SM resources free up, so the
+// next kernel's prologue (TMEM allocation, mbarrier init, tensor-map prefetch, index math) overlaps this kernel's
+// tail.  pdl_wait() blocks until all prerequisite grids have completed and their memory is visible; every kernel
+// executes it before its first access to global memory.  Both are no-ops when launched without the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace mk
 
 #define MK_CUDA_CHECK(x)                                                                      \

@@ -139,6 +139,123 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int g, int m
   }
 }
 
+// ---- staged (coalesced) epilogue -----------------------------------------------------------------------
+// The tcgen05 kernel first parks a warp's 32 x W block of fp32 accumulators in shared memory (row-major,
+// leading dimension W + 4) and then calls epilogue_rows: lane l owns columns col_base + l*CPL .. (CPL = W/32) of
+// every row, so each global load/store instruction of the warp covers ONE contiguous row segment (128-256 B)
+// instead of 32 different rows — 4-8x fewer L1 wavefronts than the thread-per-row form above, which is what
+// bounded the small ViT GEMMs (ncu: long_scoreboard + lg_throttle, profiles/r01_*).
+template <int CPL> struct VecF;
+template <> struct VecF<1> { using T = float; };
+template <> struct VecF<2> { using T = float2; };
+
+template <int CPL> __device__ __forceinline__ void ld_f(const float* p, float (&v)[CPL]) {
+  if constexpr (CPL == 2) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; } else { v[0] = *p; }
+}
+template <int CPL> __device__ __forceinline__ void ldg_f(const float* p, float (&v)[CPL]) {
+  if constexpr (CPL == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; } else { v[0] = __ldg(p); }
+}
+template <int CPL> __device__ __forceinline__ void st_f(float* p, const float (&v)[CPL]) {
+  if constexpr (CPL == 2) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); } else { *p = v[0]; }
+}
+template <int CPL> __device__ __forceinline__ void st_h(__half* p, const float (&v)[CPL]) {
+  if constexpr (CPL == 2) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0], v[1]); } else { *p = __float2half_rn(v[0]); }
+}
+template <int CPL> __device__ __forceinline__ void ld_h(const __half* p, float (&v)[CPL]) {
+  if constexpr (CPL == 2) { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(p)); v[0] = t.x; v[1] = t.y; }
+  else { v[0] = __half2float(*p); }
+}
+
+template <int EPI, int W>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int row0, int lane, int col_base,
+                                              const float* __restrict__ stage, float mean_l, float rstd_l) {
+  constexpr int CPL = W / 32;
+  constexpr int LDS = W + 4;
+  const int col = col_base + lane * CPL;
+  float bias[CPL], gam[CPL], bet[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) { bias[i] = 0.f; gam[i] = 1.f; bet[i] = 0.f; }
+  if constexpr (EPI == EPI_STORE_H || EPI == EPI_CONV) { if (p.bias) ldg_f<CPL>(p.bias + (size_t)g * p.bias_group_off + col, bias); }
+  if constexpr (EPI == EPI_RESID_F) { ldg_f<CPL>(p.bias + col, bias); ldg_f<CPL>(p.gamma + col, gam); }
+  if constexpr (EPI == EPI_LN) { ldg_f<CPL>(p.gamma + (size_t)g * p.ln_group_off + col, gam); ldg_f<CPL>(p.beta + (size_t)g * p.ln_group_off + col, bet); }
+  const bool use_aux = (EPI == EPI_CONV) && p.aux && ((p.aux_group_mask >> g) & 1);
+  const int rows = min(32, p.M - row0);
+  for (int r = 0; r < rows; ++r) {
+    const int m = row0 + r;
+    float v[CPL];
+    ld_f<CPL>(stage + r * LDS + lane * CPL, v);
+    if constexpr (EPI == EPI_STORE_H) {
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        v[i] += bias[i];
+        v[i] = (p.act == ACT_GELU) ? gelu_erf(v[i]) : ((p.act == ACT_RELU) ? fmaxf(v[i], 0.f) : v[i]);
+      }
+      st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v);
+    } else if constexpr (EPI == EPI_RESID_F) {
+      float* o = p.out_f + (size_t)m * p.out_f_ld + col;
+      float x[CPL];
+      ld_f<CPL>(o, x);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) x[i] = fmaf(gam[i], v[i] + bias[i], x[i]);
+      st_f<CPL>(o, x);
+    } else if constexpr (EPI == EPI_PATCH) {
+      const int img = m / p.tok_per_img, tk = m - img * p.tok_per_img;
+      float a[CPL];
+      ldg_f<CPL>(p.aux + (size_t)tk * p.N + col, a);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] += a[i];
+      st_f<CPL>(p.out_f + ((size_t)img * (p.tok_per_img + 1) + 1 + tk) * p.out_f_ld + col, v);
+    } else if constexpr (EPI == EPI_CONV) {
+      int pos = 0;
+      const bool valid = p.pad_h2 ? pad_valid(p, m, pos) : true;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] += bias[i];
+      if (p.res_h) {
+        float rr[CPL];
+        ld_h<CPL>(p.res_h + (size_t)g * p.res_h_group_off + (size_t)m * p.res_h_ld + col, rr);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v[i] += rr[i];
+      }
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] = apply_act(v[i], p.act);
+      if (use_aux) {
+        float a[CPL];
+        ldg_f<CPL>(p.aux + (size_t)pos * p.N + col, a);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v[i] += a[i];
+      }
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v[i] = 0.f;
+      }
+      if (p.out_f) st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v);
+      if (p.out_h) st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v);
+    } else if constexpr (EPI == EPI_STORE_F) {
+      st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v);
+    } else if constexpr (EPI == EPI_LN) {
+      const float mean = __shfl_sync(0xffffffffu, mean_l, r), rstd = __shfl_sync(0xffffffffu, rstd_l, r);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] = (v[i] - mean) * rstd * gam[i] + bet[i];
+      float* o = p.out_f ? p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col : nullptr;
+      if (o) {
+        float x[CPL];
+        ld_f<CPL>(o, x);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v[i] += x[i];
+      }
+      if (p.pad_h2) {
+        int pos;
+        if (!pad_valid(p, m, pos)) {
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) v[i] = 0.f;
+        }
+      }
+      if (o) st_f<CPL>(o, v);
+      st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v);
+    }
+  }
+}
+
 // ---- whole-row epilogues (accumulated across the chunks of one tile) ------------------------------
 // EPI_LSE: partial sum over this tile's valid columns of exp(S/T - shift)
 __device__ __forceinline__ float lse_partial(const GemmParams& p, int g, int n0, const float (&v)[32]) {

@@ -90,6 +90,8 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
                  long long b_rows, long long ldb, const GemmParams p) {
   __shared__ __align__(16) __half As[BLOCK_M][BLOCK_K + 8];
   __shared__ __half Bs[BN][BLOCK_K + 8];
+  pdl_trigger();
+  pdl_wait();
   const int g = blockIdx.z, m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BN;
   const int t = threadIdx.x;
   float acc[BN];
@@ -162,6 +164,12 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
   }
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_PDL"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  return v == 1;
+}
+
 // ---- dispatch -----------------------------------------------------------------------------------------
 static bool use_simt() {
   static int v = -1;
@@ -176,8 +184,9 @@ template <int BN, int EPI>
 static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmParams& p, cudaStream_t stream, int impl) {
   dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(p.N, BN), p.groups);
   if (impl == GEMM_IMPL_SIMT) {
-    gemm_simt_kernel<BN, EPI><<<grid, 128, 0, stream>>>(reinterpret_cast<const __half*>(A.ptr), A.rows, A.ld,
-                                                          reinterpret_cast<const __half*>(B.ptr), B.rows, B.ld, p);
+    MK_CUDA_CHECK(launch_k(gemm_simt_kernel<BN, EPI>, grid, dim3(128), 0, stream, reinterpret_cast<const __half*>(A.ptr),
+                           (long long)A.rows, (long long)A.ld, reinterpret_cast<const __half*>(B.ptr), (long long)B.rows,
+                           (long long)B.ld, p));
   } else {
     static bool attr_set = false;
     constexpr int smem = gemm_smem_bytes<BN>();
@@ -190,7 +199,7 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
     if (rc) return rc;
     rc = make_tensor_map_f16(&tmB, B.ptr, B.rows, B.cols, B.ld, BN);
     if (rc) return rc;
-    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+    MK_CUDA_CHECK(launch_k(gemm_tc_kernel<BN, EPI>, grid, dim3(GEMM_THREADS), (size_t)smem, stream, tmA, tmB, p));
   }
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;

@@ -141,6 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m0 = blockIdx.x * BLOCK_M;
   const int n0 = blockIdx.y * BN;
 
+  pdl_trigger();                 // let the next kernel's prologue overlap this kernel
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -161,6 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();                    // everything above touched no global memory; operands of the previous kernel are now visible
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -226,6 +228,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float v[32];
+    constexpr int W = BN / 2;                                  // columns owned by this warp
+    float* stage = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * (W + 4));
     if constexpr (EPI == EPI_LN) {
       float sum = 0.f;
 #pragma unroll
@@ -245,8 +249,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float rstd = rsqrtf(sq * (1.0f / BN) + p.eps);
       for (int c = c_begin; c < c_end; ++c) {
         tmem_ld32(taddr + c * 32, v);
-        ln_store_chunk(p, g, m, n0 + c * 32, v, mean, rstd);
+        float4* dst = reinterpret_cast<float4*>(stage + lane * (W + 4) + (c - c_begin) * 32);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
       }
+      __syncwarp();
+      epilogue_rows<EPI_LN, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, mean, rstd);
     } else if constexpr (EPI == EPI_LSE) {
       float s = 0.f;
       for (int c = c_begin; c < c_end; ++c) {
@@ -257,22 +265,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if constexpr (EPI == EPI_DUAL) {
       // per-warp 32x33 fp32 staging tile in the (now idle) pipeline smem: transposes "thread == row" into
       // "lane == column" so that every store instruction writes one contiguous 128-byte row segment
-      float* stage = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * 33);
+      float* stage33 = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * 33);
       float inv_r, s0, sh, dust;
       dual_row_setup(p, g, m, inv_r, s0, sh, dust);
       for (int c = c_begin; c < c_end; ++c) {
         if (n0 + c * 32 < p.n_valid) {
           tmem_ld32(taddr + c * 32, v);
-          dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage, inv_r, s0, sh, dust);
+          dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage33, inv_r, s0, sh, dust);
         }
       }
     } else {
       for (int c = c_begin; c < c_end; ++c) {
-        if (n0 + c * 32 < p.N) {
-          tmem_ld32(taddr + c * 32, v);
-          epilogue_chunk<EPI>(p, g, m, n0 + c * 32, v);
-        }
+        tmem_ld32(taddr + c * 32, v);
+        float4* dst = reinterpret_cast<float4*>(stage + lane * (W + 4) + (c - c_begin) * 32);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
       }
+      __syncwarp();
+      epilogue_rows<EPI, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, 0.f, 0.f);
     }
   }
 

@@ -2,7 +2,7 @@
 //
 //  1. outer sampling  : IT_MATCHES x "2048 of N*N cells without replacement, prob ~ final_scores".
 //                       ATen's multinomial is top-k of p / Exp(1) (an exponential race); we run the same race
-//                       with a counter-based generator (Philox4x32-10) so that each pass can regenerate the
+//                       with a counter-based generator (Philox4x32-7) so that each pass can regenerate the
 //                       noise instead of materialising the [B*IT_MATCHES, N*N] tile the reference allocates:
 //                       pass A histograms the keys (8 exponent + 3 mantissa bits), a scan finds the bin holding
 //                       the 2048-th largest key, pass B collects the <= ~2.3 k candidates at/above it, pass C
@@ -15,14 +15,14 @@
 
 namespace mk {
 
-// ---- Philox4x32-10 -------------------------------------------------------------------------------------
+// ---- Philox4x32-7 (7 rounds pass BigCrush: Salmon et al., SC'11) ----------------------------------------
 struct Philox {
   uint32_t k0, k1;
   __device__ __forceinline__ Philox(unsigned long long seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
   __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
     uint32_t a = k0, b = k1;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {
       const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
       const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
       c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
@@ -40,7 +40,7 @@ __device__ __forceinline__ float exp1_from_bits(uint32_t x) {
 __device__ __forceinline__ float u01_from_bits(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f; }
 
 __device__ __forceinline__ uint32_t race_key(float p, uint32_t bits) {
-  return (p > 0.f) ? __float_as_uint(p / exp1_from_bits(bits)) : 0u;
+  return (p > 0.f) ? __float_as_uint(__fdividef(p, exp1_from_bits(bits))) : 0u;
 }
 
 constexpr int HBINS = 2048;          // key >> 20 (sign is always 0)

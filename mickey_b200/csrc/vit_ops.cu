@@ -54,6 +54,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
                                  __half* __restrict__ out, int rows, int D, float eps, int mode, int gh, int gw) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   long long orow = row;
   if (mode == 1) {
@@ -104,12 +106,11 @@ int layernorm(const float* x, const float* w, const float* b, void* out, int row
   dim3 grid(ceil_div(rows, warps)), block(warps * 32);
   __half* o = (__half*)out;
   switch (D) {
-    case 384:  layernorm_kernel<3><<<grid, block, 0, s>>>(x, w, b, o, rows, D, eps, mode, gh, gw); break;
-    case 768:  layernorm_kernel<6><<<grid, block, 0, s>>>(x, w, b, o, rows, D, eps, mode, gh, gw); break;
-    case 1024: layernorm_kernel<8><<<grid, block, 0, s>>>(x, w, b, o, rows, D, eps, mode, gh, gw); break;
+    case 384:  MK_CUDA_CHECK(launch_k(layernorm_kernel<3>, grid, block, 0, s, x, w, b, o, rows, D, eps, mode, gh, gw)); break;
+    case 768:  MK_CUDA_CHECK(launch_k(layernorm_kernel<6>, grid, block, 0, s, x, w, b, o, rows, D, eps, mode, gh, gw)); break;
+    case 1024: MK_CUDA_CHECK(launch_k(layernorm_kernel<8>, grid, block, 0, s, x, w, b, o, rows, D, eps, mode, gh, gw)); break;
     default: set_last_error("layernorm: unsupported width %d", D); return MK_ERR_UNSUPPORTED;
   }
-  MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
 

@@ -199,6 +199,26 @@ def test_graph_replay_equals_eager():
     assert not torch.equal(data["R"], outs[0][0])
 
 
+def test_batch_invariance_and_c3_shapes():
+    """Pairs are independent: running 3 pairs as one batch must give, pair by pair, what running
+    them alone gives (bit-equal features, same pose under the same seed), here with the ViT-B backbone and the
+    1024-hypothesis budget of BASELINE config 3 at full 720x540 resolution."""
+    cfg, model = _model("vitb", 16, 64, 0)
+    batch = synthetic_pair(3, 720, 540, seed=21)
+    full = _to_dev(dict(batch))
+    torch.manual_seed(7)
+    model(full)
+    torch.cuda.synchronize()
+    assert tuple(full["final_scores"].shape) == (3, 1938, 1938) and bool(torch.isfinite(full["R"]).all())
+    for b in (0, 2):
+        one = _to_dev({k: v[b:b + 1] for k, v in batch.items()})
+        torch.manual_seed(7)
+        model(one)
+        for k in ("dsc0", "dsc1", "kps0", "depth_kp1", "scr0"):
+            assert torch.equal(one[k][0], full[k][b]), k
+        assert rel_err(one["final_scores"][0], full["final_scores"][b]) < 1e-6
+
+
 def test_full_forward_contract_and_properties():
     """model(data) on a BASELINE-size pair: every data-dict key of the reference is produced with the
     reference's shapes, and the N x N outputs obey their algebraic identities."""
