@@ -88,7 +88,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
   const int n_tiles = (T + FA_BK - 1) / FA_BK;
   const int row_base = im * T;
 
-  pdl_trigger();
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
     mbar_init(q_full, 1);
@@ -245,6 +244,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
     // epilogue: O / l -> fp16
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc_fence_after();
+    pdl_trigger();
     const int q = q0 + warp * 32 + lane;
     const float inv = 1.0f / l_run;
     __half* dst = out + ((long long)(row_base + q)) * D + head * FA_D;

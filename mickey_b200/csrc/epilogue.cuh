@@ -180,6 +180,19 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
   if constexpr (EPI == EPI_LN) { ldg_f<CPL>(p.gamma + (size_t)g * p.ln_group_off + col, gam); ldg_f<CPL>(p.beta + (size_t)g * p.ln_group_off + col, bet); }
   const bool use_aux = (EPI == EPI_CONV) && p.aux && ((p.aux_group_mask >> g) & 1);
   const int rows = min(32, p.M - row0);
+  // per-row index math is done once by lane r (for row r) and broadcast with a shuffle inside the loop
+  int my_pos = 0, my_valid = 1, my_orow = 0;
+  {
+    const int mr = row0 + lane;
+    if constexpr (EPI == EPI_CONV || EPI == EPI_LN) {
+      if (p.pad_h2) { int pos; my_valid = pad_valid(p, mr, pos) ? 1 : 0; my_pos = pos; }
+    }
+    if constexpr (EPI == EPI_PATCH) {
+      const int img = mr / p.tok_per_img;
+      my_pos = mr - img * p.tok_per_img;                 // token index inside the image
+      my_orow = img * (p.tok_per_img + 1) + 1 + my_pos;  // row of the token matrix (cls rows skipped)
+    }
+  }
   for (int r = 0; r < rows; ++r) {
     const int m = row0 + r;
     float v[CPL];
@@ -199,15 +212,15 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
       for (int i = 0; i < CPL; ++i) x[i] = fmaf(gam[i], v[i] + bias[i], x[i]);
       st_f<CPL>(o, x);
     } else if constexpr (EPI == EPI_PATCH) {
-      const int img = m / p.tok_per_img, tk = m - img * p.tok_per_img;
+      const int tk = __shfl_sync(0xffffffffu, my_pos, r), orow = __shfl_sync(0xffffffffu, my_orow, r);
       float a[CPL];
       ldg_f<CPL>(p.aux + (size_t)tk * p.N + col, a);
 #pragma unroll
       for (int i = 0; i < CPL; ++i) v[i] += a[i];
-      st_f<CPL>(p.out_f + ((size_t)img * (p.tok_per_img + 1) + 1 + tk) * p.out_f_ld + col, v);
+      st_f<CPL>(p.out_f + (size_t)orow * p.out_f_ld + col, v);
     } else if constexpr (EPI == EPI_CONV) {
-      int pos = 0;
-      const bool valid = p.pad_h2 ? pad_valid(p, m, pos) : true;
+      const int pos = __shfl_sync(0xffffffffu, my_pos, r);
+      const bool valid = __shfl_sync(0xffffffffu, my_valid, r) != 0;
 #pragma unroll
       for (int i = 0; i < CPL; ++i) v[i] += bias[i];
       if (p.res_h) {
@@ -243,12 +256,9 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
 #pragma unroll
         for (int i = 0; i < CPL; ++i) v[i] += x[i];
       }
-      if (p.pad_h2) {
-        int pos;
-        if (!pad_valid(p, m, pos)) {
+      if (__shfl_sync(0xffffffffu, my_valid, r) == 0) {
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) v[i] = 0.f;
-        }
+        for (int i = 0; i < CPL; ++i) v[i] = 0.f;
       }
       if (o) st_f<CPL>(o, v);
       st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v);

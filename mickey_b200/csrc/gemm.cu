@@ -180,6 +180,24 @@ static bool use_simt() {
   return v == 1;
 }
 
+template <int BN, int EPI, int STAGES>
+static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  if (!attr_set) {
+    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  MK_CUDA_CHECK(launch_k(gemm_tc_kernel<BN, EPI, STAGES>, grid, dim3(GEMM_THREADS), (size_t)smem, stream, tmA, tmB, p));
+  return MK_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
 template <int BN, int EPI>
 static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmParams& p, cudaStream_t stream, int impl) {
   dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(p.N, BN), p.groups);
@@ -188,18 +206,15 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
                            (long long)A.rows, (long long)A.ld, reinterpret_cast<const __half*>(B.ptr), (long long)B.rows,
                            (long long)B.ld, p));
   } else {
-    static bool attr_set = false;
-    constexpr int smem = gemm_smem_bytes<BN>();
-    if (!attr_set) {
-      MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
     CUtensorMap tmA, tmB;
     int rc = make_tensor_map_f16(&tmA, A.ptr, A.rows, A.cols, A.ld, BLOCK_M);
     if (rc) return rc;
     rc = make_tensor_map_f16(&tmB, B.ptr, B.rows, B.cols, B.ld, BN);
     if (rc) return rc;
-    MK_CUDA_CHECK(launch_k(gemm_tc_kernel<BN, EPI>, grid, dim3(GEMM_THREADS), (size_t)smem, stream, tmA, tmB, p));
+    // grids that give every SM at most ~one CTA run the deep ring; bigger grids keep two CTAs per SM
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    const bool deep = ctas <= (long long)sm_count() * 5 / 4 && p.k_chunks > 3;
+    return deep ? launch_tc<BN, EPI, 6>(grid, tmA, tmB, p, stream) : launch_tc<BN, EPI, 3>(grid, tmA, tmB, p, stream);
   }
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;

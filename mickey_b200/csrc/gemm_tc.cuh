@@ -24,12 +24,14 @@ namespace mk {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;        // 64 fp16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_STAGES = 3;
 constexpr int GEMM_THREADS = 256;
 
-template <int BN>
+// STAGES = 3: two CTAs resident per SM (large grids: one CTA's epilogue overlaps the other's main loop)
+// STAGES = 6: one CTA per SM with twice the bytes in flight (grids of <= ~1 CTA per SM, where the 3-deep ring was
+//             latency-bound: ViT proj / fc2 at B=1 moved 64 GB/s per SM)
+template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return GEMM_STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -118,8 +120,8 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_f16() {
 }
 
 // ---- kernel ------------------------------------------------------------------------------------------
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+template <int BN, int EPI, int GEMM_STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, (GEMM_STAGES <= 3) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -141,7 +143,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m0 = blockIdx.x * BLOCK_M;
   const int n0 = blockIdx.y * BN;
 
-  pdl_trigger();                 // let the next kernel's prologue overlap this kernel
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -226,6 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m = m0 + row;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    pdl_trigger();               // main loop done: the next kernel's CTAs may start their prologue under our epilogue
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float v[32];
     constexpr int W = BN / 2;                                  // columns owned by this warp

@@ -66,17 +66,22 @@ linattn_kv_kernel(const float* __restrict__ qkv, float* __restrict__ kvout, int 
   if (vh == 0) o[256 + d] = ksum;
 }
 
-// out[i] = sum_c part[c][i] over the row chunks, one thread per output element.  grid (G, n_img).
-__global__ void __launch_bounds__(256)
+// out[i] = sum_c part[c][i] over the row chunks in a fixed order, one thread per output element.
+// grid (ceil(2176/128), G, n_img), 128 threads; 8 independent loads in flight per thread.
+__global__ void __launch_bounds__(128)
 linattn_kv_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int G, int chunks) {
-  const int g = blockIdx.x, im = blockIdx.y;
-  const float* src = part + ((long long)im * G + g) * chunks * (8 * 272);
-  float* dst = out + ((long long)im * G + g) * (8 * 272);
-  for (int i = threadIdx.x; i < 8 * 272; i += 256) {
-    float a = 0.f;
-    for (int c = 0; c < chunks; ++c) a += src[(long long)c * (8 * 272) + i];
-    dst[i] = a;
+  const int g = blockIdx.y, im = blockIdx.z;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= 8 * 272) return;
+  const float* src = part + ((long long)im * G + g) * chunks * (8 * 272) + i;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int c = 0;
+  for (; c + 8 <= chunks; c += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += src[(long long)(c + k) * (8 * 272)];
   }
+  for (; c < chunks; ++c) acc[0] += src[(long long)c * (8 * 272)];
+  out[((long long)im * G + g) * (8 * 272) + i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 // Linear attention, query half (attention.py:52,60-61): msg = (Q KV) / (Q . Ksum + eps) * L, Q = elu(q)+1.
@@ -130,7 +135,7 @@ int linattn_kv(const float* qkv, float* kv_part, float* kv, int n_img, int G, in
   const int chunks = linattn_kv_chunks(h2, w2);
   linattn_kv_kernel<<<dim3(chunks, G, n_img), 256, 0, s>>>(qkv, kv_part, G, h2, w2);
   MK_CUDA_CHECK(cudaGetLastError());
-  linattn_kv_reduce_kernel<<<dim3(G, n_img), 256, 0, s>>>(kv_part, kv, G, chunks);
+  linattn_kv_reduce_kernel<<<dim3(ceil_div(8 * 272, 128), G, n_img), 128, 0, s>>>(kv_part, kv, G, chunks);
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }

@@ -54,8 +54,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
                                  __half* __restrict__ out, int rows, int D, float eps, int mode, int gh, int gw) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   if (row >= rows) return;
   long long orow = row;
   if (mode == 1) {

@@ -344,46 +344,65 @@ class Engine:
             self._stream()), "mk_forward")
 
     def forward(self, image0, image1, K0, K1, seed: int, use_graph: bool = True):
-        """Whole hot path (extract -> match -> solve) for a batch of pairs.  Returns the dict of STATIC output
-        tensors of this (B, H, W) geometry: they are overwritten by the next call with the same geometry."""
+        """Whole hot path (extract -> match -> solve) for a batch of pairs.
+
+        Returns the dict of STATIC output tensors of this (B, H, W) geometry.  Two buffer sets alternate, so the
+        tensors of one call stay valid until the call after the next one with the same geometry.  Host (pinned)
+        inputs are copied H2D on a side stream into the other buffer set while the previous call is still
+        computing; device inputs are copied D2D on the main stream."""
         B = image0.shape[0]
         H, W = image0.shape[-2], image0.shape[-1]
         self._ws_for(B, H, W)
-        key = (B, H, W)
         if not hasattr(self, "_graphs"):
-            self._graphs = {}
+            self._graphs, self._slot, self._copy_stream = {}, {}, torch.cuda.Stream(device=self.device)
+        slot = self._slot.get((B, H, W), 0)
+        self._slot[(B, H, W)] = slot ^ 1
+        key = (B, H, W, slot)
         ent = self._graphs.get(key)
         if ent is None or ent["ws_ptr"] != self.ws.data_ptr():
-            ent = {"st": self._static_buffers(B, H, W), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(), "calls": 0}
+            ent = {"st": self._static_buffers(B, H, W), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(),
+                   "calls": 0, "done": None}
             self._graphs[key] = ent
         st = ent["st"]
-        st["images"][:B].copy_(image0, non_blocking=True)      # H2D straight from (pinned) host memory, or D2D
-        st["images"][B:].copy_(image1, non_blocking=True)
-        st["K0"].copy_(K0, non_blocking=True)
-        st["K1"].copy_(K1, non_blocking=True)
+        main = torch.cuda.current_stream()
+        if image0.device.type == "cpu":
+            cs = self._copy_stream
+            if ent["done"] is not None:
+                cs.wait_event(ent["done"])              # the graph that last read this input buffer has finished
+            with torch.cuda.stream(cs):
+                st["images"][:B].copy_(image0, non_blocking=True)
+                st["images"][B:].copy_(image1, non_blocking=True)
+                st["K0"].copy_(K0, non_blocking=True)
+                st["K1"].copy_(K1, non_blocking=True)
+            main.wait_stream(cs)
+        else:
+            st["images"][:B].copy_(image0, non_blocking=True)
+            st["images"][B:].copy_(image1, non_blocking=True)
+            st["K0"].copy_(K0, non_blocking=True)
+            st["K1"].copy_(K1, non_blocking=True)
         seed = (int(seed) & (2 ** 64 - 1)) or 1
         if not use_graph:
             self._call_forward(st, B, H, W, seed)
-            return st
-        if ent["graph"] is None:
-            # the first call runs eagerly (lazy one-time initialisation inside the library: function attributes,
-            # TMA descriptors), the second call is captured, later calls replay
-            if ent["calls"] == 0:
-                l0 = self.launch_count
-                self._call_forward(st, B, H, W, seed)
-                ent["launches"] = self.launch_count - l0
-                ent["calls"] = 1
-                return st
+        elif ent["graph"] is None and ent["calls"] == 0:
+            # first call of this buffer set runs eagerly (one-time lazy initialisation inside the library:
+            # function attributes, TMA descriptors); the second call is captured, later calls replay
+            l0 = self.launch_count
+            self._call_forward(st, B, H, W, seed)
+            ent["launches"] = self.launch_count - l0
+            ent["calls"] = 1
+        else:
             _lib.check(self.lib.mk_set_seed(self.h, C.c_ulonglong(seed), self._stream()), "mk_set_seed")
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._call_forward(st, B, H, W, 0)          # seed 0 = continue the device-side sequence
-            ent["graph"] = g
-            self.graph_replays = getattr(self, "graph_replays", 0)
-        _lib.check(self.lib.mk_set_seed(self.h, C.c_ulonglong(seed), self._stream()), "mk_set_seed")
-        ent["graph"].replay()
-        self.graph_replays += 1
-        self.graph_launches = getattr(self, "graph_launches", 0) + ent["launches"]
+            if ent["graph"] is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._call_forward(st, B, H, W, 0)      # seed 0 = continue the device-side sequence
+                ent["graph"] = g
+            ent["graph"].replay()
+            self.graph_replays = getattr(self, "graph_replays", 0) + 1
+            self.graph_launches = getattr(self, "graph_launches", 0) + ent["launches"]
+        if ent["done"] is None:
+            ent["done"] = torch.cuda.Event()
+        ent["done"].record(main)
         return st
 
     def solve(self, final_scores, kps, depth, K0, K1, seed: int, outer_idx=None, inner_idx=None, want_extras=False):

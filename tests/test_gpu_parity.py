@@ -181,13 +181,13 @@ def test_graph_replay_equals_eager():
     counter-based generator is re-seeded in front of the replay)."""
     cfg, model = _model("vits", 4, 16, 0)
     outs = []
-    for i in range(4):
+    for i in range(6):
         data = _to_dev(synthetic_pair(2, 210, 196, seed=5))
         torch.manual_seed(42)
         R, t = model(data)
         torch.cuda.synchronize()
         outs.append((R.clone(), t.clone(), data["dsc0"].clone(), data["final_scores"].clone(), data["inliers"].clone()))
-    assert model._engine()._graphs[(2, 210, 196)]["graph"] is not None
+    assert all(model._engine()._graphs[(2, 210, 196, slot)]["graph"] is not None for slot in (0, 1))
     for o in outs[1:]:
         assert torch.equal(o[2], outs[0][2])
         assert rel_err(o[3], outs[0][3]) < 1e-6              # row/col sums use float atomics
