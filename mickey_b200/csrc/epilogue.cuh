@@ -193,6 +193,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
       my_orow = img * (p.tok_per_img + 1) + 1 + my_pos;  // row of the token matrix (cls rows skipped)
     }
   }
+#pragma unroll 4                                  // 4 rows in flight per lane: independent chains for ILP
   for (int r = 0; r < rows; ++r) {
     const int m = row0 + r;
     float v[CPL];

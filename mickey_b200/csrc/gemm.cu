@@ -166,7 +166,10 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
 
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MICKEY_PDL"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  // opt-in: measured on B200 (profiles/r01_notes.md) PDL was 2-3 % slower for this pipeline inside a CUDA graph —
+  // early-launched CTAs hold shared memory / TMEM while they wait, which costs the primary kernel's later waves more
+  // than the overlapped prologues save.
+  if (v < 0) { const char* e = getenv("MICKEY_PDL"); v = (e && strcmp(e, "1") == 0) ? 1 : 0; }
   return v == 1;
 }
 
