@@ -182,7 +182,10 @@ def sine_table_padded(gh: int, gw: int, d_model: int = 128) -> torch.Tensor:
 class Engine:
     """One C handle + packed weights + workspace for a fixed (cfg, device)."""
 
-    def __init__(self, cfg, device):
+    def __init__(self, cfg, device, side_stream: bool = False):
+        """side_stream=True gives the engine its own CUDA stream for forward(): two such engines (see
+        MickeyRelativePose.pipeline_depth) keep two steps in flight, so the many kernels of one step that cannot fill
+        148 SMs at B=1 share the GPU with the next step's."""
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = torch.device(device)
@@ -193,6 +196,8 @@ class Engine:
         _lib.check(self.lib.mk_create(self.device.index or 0, C.byref(self.mkcfg), C.byref(h)), "mk_create")
         self.h = h
         self.packed: Dict[str, torch.Tensor] = {}
+        self.stream = torch.cuda.Stream(device=self.device) if side_stream else None
+        self.assume_inputs_ready = False
         self._raw_pos = None
         self.geo = None
         self.ws = None
@@ -206,12 +211,18 @@ class Engine:
             pass
 
     # -- weights ---------------------------------------------------------------------------------------------
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
-        with torch.no_grad():
-            self.packed = pack_weights(sd, self.cfg, self.device)
-            self._raw_pos = (sd[BACKBONE + "pos_embed"].detach().to(self.device).float(),
-                             sd[BACKBONE + "cls_token"].detach().to(self.device).float(),
-                             sd[BACKBONE + "patch_embed.proj.bias"].detach().to(self.device).float())
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], share_with: "Engine" = None):
+        """share_with: another engine on the same device whose packed weight tensors are registered here too
+        (one copy of the weights in HBM for all pipeline slots)."""
+        if share_with is not None:
+            self.packed = {k: v for k, v in share_with.packed.items() if k not in ("patch.posb", "patch.clspos", "head.pe")}
+            self._raw_pos = share_with._raw_pos
+        else:
+            with torch.no_grad():
+                self.packed = pack_weights(sd, self.cfg, self.device)
+                self._raw_pos = (sd[BACKBONE + "pos_embed"].detach().to(self.device).float(),
+                                 sd[BACKBONE + "cls_token"].detach().to(self.device).float(),
+                                 sd[BACKBONE + "patch_embed.proj.bias"].detach().to(self.device).float())
         for name, t in self.packed.items():
             self._register(name, t)
         self.geo = None
@@ -364,7 +375,17 @@ class Engine:
                    "calls": 0, "done": None}
             self._graphs[key] = ent
         st = ent["st"]
-        main = torch.cuda.current_stream()
+        caller = torch.cuda.current_stream()
+        main = self.stream if self.stream is not None else caller
+        if self.stream is not None and image0.device.type != "cpu" and not self.assume_inputs_ready:
+            main.wait_stream(caller)                    # device inputs may still be being produced on the caller's stream
+        with torch.cuda.stream(main):
+            self._forward_on(main, ent, st, image0, image1, K0, K1, B, H, W, seed, use_graph)
+        if self.stream is not None:
+            caller.wait_event(ent["done"])              # outputs are safe to consume on the caller's stream
+        return st
+
+    def _forward_on(self, main, ent, st, image0, image1, K0, K1, B, H, W, seed, use_graph):
         if image0.device.type == "cpu":
             cs = self._copy_stream
             if ent["done"] is not None:
@@ -403,7 +424,6 @@ class Engine:
         if ent["done"] is None:
             ent["done"] = torch.cuda.Event()
         ent["done"].record(main)
-        return st
 
     def solve(self, final_scores, kps, depth, K0, K1, seed: int, outer_idx=None, inner_idx=None, want_extras=False):
         """kps [2B,2,N], depth [2B,1,N] as produced by extract (image0 rows first)."""

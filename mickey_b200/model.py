@@ -187,6 +187,26 @@ class MickeyRelativePose(nn.Module):
     def is_eval_model(self, is_eval):
         return None        # BatchNorm is folded at load time: always eval semantics
 
+    def _engine_pool(self):
+        """pipeline_depth engines (default 1).  With depth 2, consecutive forward() calls alternate between two engines
+        that own separate workspaces, CUDA graphs, RNG state and streams but share one copy of the packed weights."""
+        depth = int(getattr(self, "pipeline_depth", 1))
+        first = self._engine()
+        pool = self.__dict__.setdefault("_pool", [])
+        if len(pool) != depth - 1 or self.__dict__.get("_pool_version") != self._eng_version or (pool and pool[0].device != first.device):
+            pool.clear()
+            for _ in range(depth - 1):
+                e = Engine(self.cfg, first.device, side_stream=True)
+                e.load_state_dict(None, share_with=first)
+                pool.append(e)
+            self.__dict__["_pool_version"] = self._eng_version
+        if depth > 1 and first.stream is None:
+            first.stream = torch.cuda.Stream(device=first.device)
+        engines = [first] + pool
+        for e in engines:
+            e.assume_inputs_ready = bool(getattr(self, "assume_inputs_ready", False))
+        return engines
+
     def _engine(self) -> Engine:
         dev = next(self.parameters()).device
         if dev.type != "cuda":
@@ -227,7 +247,10 @@ class MickeyRelativePose(nn.Module):
         tensors like the reference does."""
         if getattr(self, "staged", False):
             return self.forward_staged(data, return_inliers)
-        eng = self._engine()
+        pool = self._engine_pool()
+        turn = self.__dict__.get("_turn", 0)
+        self.__dict__["_turn"] = turn + 1
+        eng = pool[turn % len(pool)]
         im0, im1 = data["image0"], data["image1"]
         B = im0.shape[0]
         seed = int(torch.randint(1, 2 ** 62, (1,)).item())
