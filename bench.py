@@ -203,6 +203,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("MICKEY_PIPELINE_DEPTH", "3")),
+                    help="steps kept in flight on alternating engines/streams (1 = strictly one step at a time)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -287,9 +289,9 @@ def main():
     latency_ms = timed(step_device, args.steps, True) / args.steps
     eng = model._engine()
     # (2) throughput: two steps in flight on alternating engines/streams (inputs are constant device tensors)
-    model.pipeline_depth = 2
+    model.pipeline_depth = max(1, args.depth)
     model.assume_inputs_ready = True
-    for _ in range(max(args.warmup, 8)):        # each of the 2 engines x 2 buffer sets: one eager call + one capture
+    for _ in range(max(args.warmup, 4 * max(1, args.depth))):        # each of the 2 engines x 2 buffer sets: one eager call + one capture
         step_device()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -301,7 +303,7 @@ def main():
     clock_info = clocks.finish() if rank == 0 else None
     ws_bytes = sum(int(e.ws.numel()) for e in engines)
 
-    for _ in range(8):
+    for _ in range(4 * max(1, args.depth)):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps, False)
     model.pipeline_depth = 1
@@ -368,9 +370,9 @@ def main():
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tensor core), f32 matcher+solver", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "parallelism": f"dp{world} (pairs sharded, one all-gather of [B,13] poses)",
-                   "pipelining": "2 steps in flight (two engines on alternating CUDA streams); latency_ms_single_step is the "
+                   "pipelining": f"{max(1, args.depth)} steps in flight (engines on alternating CUDA streams); latency_ms_single_step is the "
                                  "un-pipelined time of one step with the L2 flushed in between",
-                   "l2": f"no flush in pipelined mode: each step streams its {ws_bytes // 2 / 1e6:.0f} MB workspace + 46 MB of "
+                   "l2": f"no flush in pipelined mode: each step streams its {ws_bytes // max(1, args.depth) / 1e6:.0f} MB workspace + 46 MB of "
                          "N x N outputs + 125 MB of weights, larger than the 126 MB L2; the latency run flushes a 256 MiB buffer",
                    "weights": "seeded random init", "launch": "one mk_forward C call per step, replayed from a CUDA graph"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_ms / args.steps,

@@ -192,25 +192,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
 #pragma unroll
         for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : -INFINITY;
       }
-      float mx = -INFINITY;                        // max of the RAW logits; scale_log2 > 0 commutes with max
+      // max of the RAW logits (scale_log2 > 0 commutes with max); 8 independent chains instead of one 128-long one
+      float mxa[8];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, s[i]);
+      for (int k = 0; k < 8; ++k) mxa[k] = s[k];
+#pragma unroll
+      for (int i = 8; i < 128; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[i]);
+      float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       mx *= scale_log2;
       float alpha = 1.0f;
       const bool move = (mx > m_ref + 8.0f);       // always true for j == 0 (m_ref = -inf)
       if (move) { alpha = ex2_approx(m_ref - mx); m_ref = mx; }
-      // p = 2^(s*scale - m_ref): one FFMA + one MUFU.EX2 per element, two partial sums for ILP
-      float sum0 = 0.f, sum1 = 0.f;
+      // p = 2^(s*scale - m_ref): one FFMA + one MUFU.EX2 per element, 8 partial sums for ILP
+      float sa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_ref;
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         const float p0 = ex2_approx(fmaf(s[2 * i], scale_log2, neg_m)), p1 = ex2_approx(fmaf(s[2 * i + 1], scale_log2, neg_m));
-        sum0 += p0; sum1 += p1;
+        sa[(2 * i) & 7] += p0; sa[(2 * i + 1) & 7] += p1;
         __half2 h = __floats2half2_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&h);
       }
-      const float sum = sum0 + sum1;
+      const float sum = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
       l_run = l_run * alpha + sum;
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);           // P buffer free, O quiescent
