@@ -7,16 +7,21 @@
 
 namespace mk {
 
-// exact-erf GELU (reference layers/mlp.py:23 nn.GELU()): erf by Abramowitz-Stegun 7.1.26, |abs err| < 1.5e-7
+// exact-erf GELU (reference layers/mlp.py:23 nn.GELU()): erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7 in
+// exact arithmetic).  rcp/ex2 are the single-instruction MUFU approximations (1-2 ulp): the IEEE __frcp_rn / __expf
+// forms expand to Newton iterations and range fix-ups that made this epilogue ~30 instructions per element (ncu).
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx_f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float erf_abs = fmaf(-poly * t, ex2_approx_f(-1.4426950408889634f * z * z), 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, copysignf(erf_abs, x), hx);
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {

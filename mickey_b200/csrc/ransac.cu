@@ -127,6 +127,9 @@ sampler_threshold_kernel(const unsigned int* __restrict__ hist, int n_streams, i
 }
 
 // ---- pass B: collect candidates (bin >= threshold) ---------------------------------------------------------
+// key >= tau  <=>  E <= p / tau  <=>  u <= 1 - exp(-p / tau), so almost every (cell, stream) is rejected with one
+// MUFU.EX2 and a compare (no log, no division); the exact key is recomputed only for the ~0.06 % that pass the
+// (slightly widened) cheap test, and the exact bin test of pass A decides.
 __global__ void __launch_bounds__(SAMP_THREADS)
 sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
                        const int* __restrict__ thr, unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt,
@@ -135,21 +138,37 @@ sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, co
   const float* p = fs + (long long)b * cells;
   const Philox rng(*seed_ptr);
   int T[4];
+  float inv_tau[4];                    // 1 / tau, tau = lower edge of the threshold bin
 #pragma unroll
-  for (int j = 0; j < 4; ++j) T[j] = (sg * 4 + j < IM) ? thr[(long long)b * IM + sg * 4 + j] : 0x7fffffff;
+  for (int j = 0; j < 4; ++j) {
+    T[j] = (sg * 4 + j < IM) ? thr[(long long)b * IM + sg * 4 + j] : 0x7fffffff;
+    const float tau = __uint_as_float((uint32_t)(T[j] < 2047 ? T[j] : 2047) << 20);
+    inv_tau[j] = (sg * 4 + j < IM) ? 1.0f / tau : 0.0f;
+  }
   const long long e0 = (long long)blockIdx.x * SAMP_ELEMS_PER_BLOCK;
   const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
   for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) {
     const float pv = p[e];
     if (pv > 0.f) {
       const uint4 r = rng((uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)sg, (uint32_t)b);
-      const uint32_t k[4] = {race_key(pv, r.x), race_key(pv, r.y), race_key(pv, r.z), race_key(pv, r.w)};
+      const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if ((int)(k[j] >> 20) >= T[j]) {
-          const long long s = (long long)b * IM + sg * 4 + j;
-          const unsigned int slot = atomicAdd(cnt + s, 1u);
-          if (slot < (unsigned)cap) cand[s * cap + slot] = ((unsigned long long)k[j] << 32) | (uint32_t)e;
+        // u <= (1 - exp(-y)) * (1 + 2^-10) + 2^-30 with y = p / tau: a superset of the exact condition.  For small y
+        // 1 - exp(-y) <= y is used instead (1 - q would cancel catastrophically in fp32).
+        const float y = pv * inv_tau[j];
+        float q;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(-1.4426950408889634f * y));
+        const float prob = (y < 0.01f) ? y : 1.0f - q;
+        const float uth = fmaf(prob, 1.0009765625f, 9.3132257e-10f);
+        const float u = ((float)bits[j] + 0.5f) * 2.3283064365386963e-10f;
+        if (u <= uth) {
+          const uint32_t k = race_key(pv, bits[j]);
+          if ((int)(k >> 20) >= T[j]) {
+            const long long s = (long long)b * IM + sg * 4 + j;
+            const unsigned int slot = atomicAdd(cnt + s, 1u);
+            if (slot < (unsigned)cap) cand[s * cap + slot] = ((unsigned long long)k << 32) | (uint32_t)e;
+          }
         }
       }
     }
