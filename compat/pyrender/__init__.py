@@ -1,0 +1,6 @@
+"""Import-only shim: pyrender is imported at module top by the reference's lib/utils/visualization.py but only used by the
+optional 3-D rendering (--generate_3D_vis); any attribute access raises."""
+
+
+def __getattr__(name):
+    raise ImportError("pyrender is not installed in this image; 3-D visualisation is unavailable")
