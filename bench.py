@@ -33,6 +33,13 @@ from mickey_b200.weights import synthetic_checkpoint, synthetic_state_dict  # no
 
 H_IMG, W_IMG = 720, 540
 VARIANT, IT_MATCHES, IT_RANSAC = "vits", 8, 64
+PAIRS_PER_STEP = 1
+WORKLOADS = {
+    # name: (variant, it_matches, it_ransac, pairs per GPU per step, description)
+    "c2": ("vits", 8, 64, 1, "BASELINE configs[1]: single 720x540 synthetic pair, ViT-S/14, 512 hypotheses (8x64), 2048 sampled matches"),
+    "c3": ("vitb", 16, 64, 32, "BASELINE configs[2]: batch of 32 synthetic 720x540 pairs, ViT-B/14, 1024 hypotheses (16x64), 2048 sampled matches"),
+}
+VIT_DIMS = {"vits": (384, 12), "vitb": (768, 12), "vitl": (1024, 24)}
 K_TOY = [[549.7, 0.0, 268.7], [0.0, 549.7, 351.8], [0.0, 0.0, 1.0]]
 WORKLOAD = "BASELINE configs[1]: single 720x540 synthetic pair, ViT-S/14, 512 hypotheses (8x64), 2048 sampled matches"
 
@@ -203,9 +210,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="c2 (default, the configuration the metric is quoted on) or c3 (B=32, ViT-B; extra data point)")
     ap.add_argument("--depth", type=int, default=int(os.environ.get("MICKEY_PIPELINE_DEPTH", "3")),
                     help="steps kept in flight on alternating engines/streams (1 = strictly one step at a time)")
     args = ap.parse_args()
+    global VARIANT, IT_MATCHES, IT_RANSAC, WORKLOAD, PAIRS_PER_STEP
+    VARIANT, IT_MATCHES, IT_RANSAC, PAIRS_PER_STEP, WORKLOAD = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -225,7 +236,7 @@ def main():
     cfg = mickey_cfg(VARIANT, IT_MATCHES, IT_RANSAC)
     model = build_model(cfg, synthetic_checkpoint(cfg, seed=0, with_backbone=True))
     model.static_outputs = True     # hand out the engine's static output buffers (no per-call clones)
-    B = 1
+    B = PAIRS_PER_STEP
     im0, im1, K = synthetic_pair(B, seed=rank)
     dev_data = {"image0": im0.to(dev), "image1": im1.to(dev), "K_color0": K.to(dev), "K_color1": K.to(dev)}
     pin = {"image0": im0.pin_memory(), "image1": im1.pin_memory()}
@@ -331,7 +342,8 @@ def main():
     peaks = measured_peaks()
     value = world * B * args.steps / (total_ms / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
-    flops, nbytes = work_model(n_pairs=B)
+    flops, nbytes = work_model(D=VIT_DIMS[VARIANT][0], depth=VIT_DIMS[VARIANT][1], n_pairs=B)
+    nbytes["solve.sample_outer"] = B * (H_IMG // 14 * (W_IMG // 14)) ** 2 * 4
 
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -388,7 +400,7 @@ def main():
         "roofline_matcher": roof("match.dual_softmax"), "roofline_sampler": roof("solve.sample_outer"),
         "stage_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
         cores = cpu_threads()
         durs = cpu_reference_run(n_timed=3, n_warm=1, threads=cores, budget_s=25.0)
         line["cpu_baseline"] = {"value": len(durs) / sum(durs), "unit": "pairs/s", "cores": cores, "kind": "port",
