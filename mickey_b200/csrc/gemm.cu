@@ -195,6 +195,30 @@ static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return MK_OK;
 }
 
+template <int BN, int EPI>
+static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  constexpr int smem = gemm_persistent_smem_bytes<BN>();
+  if (!attr_set) {
+    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long total = (long long)tiles.x * tiles.y * tiles.z;
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
+  MK_CUDA_CHECK(launch_k(gemm_tc_persistent_kernel<BN, EPI>, dim3(grid), dim3(PERSIST_THREADS), (size_t)smem, stream, tmA, tmB, p,
+                         (int)tiles.x, (int)tiles.y));
+  return MK_OK;
+}
+
+static bool persistent_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_PERSISTENT"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  return v == 1;
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -217,7 +241,10 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
     // grids that give every SM at most ~one CTA run the deep ring; bigger grids keep two CTAs per SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     const bool deep = ctas <= (long long)sm_count() * 5 / 4 && p.k_chunks > 3;
-    return deep ? launch_tc<BN, EPI, 6>(grid, tmA, tmB, p, stream) : launch_tc<BN, EPI, 3>(grid, tmA, tmB, p, stream);
+    if (deep) return launch_tc<BN, EPI, 6>(grid, tmA, tmB, p, stream);
+    // more tiles than ~1.25 per SM: persistent tile loop with the accumulator double-buffered in TMEM
+    if (persistent_enabled()) return launch_persistent<BN, EPI>(grid, tmA, tmB, p, stream);
+    return launch_tc<BN, EPI, 3>(grid, tmA, tmB, p, stream);
   }
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;

@@ -119,6 +119,81 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_f16() {
   return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// ---- tile epilogue -----------------------------------------------------------------------------------
+// One warp's share of a 128 x BN accumulator tile: TMEM lanes 32q..32q+31 (its quadrant q) and half of the tile's
+// 32-column chunks (warps q and q+4 split the columns).  `stage` is the warp's private 32 x (BN/2 + 4) fp32
+// staging block; `release()` is called as soon as the accumulator has been read for the last time (the persistent
+// kernel hands the TMEM buffer back to the MMA warp there, before the global stores).
+template <int BN, int EPI, typename Release>
+__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0, int n0, int n_tile, int q, int half,
+                                              int lane, uint32_t tmem_acc, float* stage, Release release) {
+  constexpr int CHUNKS = BN / 32;
+  constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
+  constexpr int W = BN / 2;                      // columns owned by this warp
+  const int c_begin = half * CPH;
+  const int c_end = (c_begin + CPH < CHUNKS) ? c_begin + CPH : CHUNKS;
+  const int m = m0 + q * 32 + lane;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+  float v[32];
+  if constexpr (EPI == EPI_LN) {
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
+    }
+    const float mean = sum * (1.0f / BN);
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq += d * d; }
+    }
+    const float rstd = rsqrtf(sq * (1.0f / BN) + p.eps);
+    for (int c = c_begin; c < c_end; ++c) {
+      tmem_ld32(taddr + c * 32, v);
+      float4* dst = reinterpret_cast<float4*>(stage + lane * (W + 4) + (c - c_begin) * 32);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+    }
+    release();
+    __syncwarp();
+    epilogue_rows<EPI_LN, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, mean, rstd);
+  } else if constexpr (EPI == EPI_LSE) {
+    float s = 0.f;
+    for (int c = c_begin; c < c_end; ++c) {
+      tmem_ld32(taddr + c * 32, v);
+      s += lse_partial(p, g, n0 + c * 32, v);
+    }
+    release();
+    if (m < p.n_valid) p.row_sum[((size_t)g * p.n_valid + m) * p.sum_slots + n_tile * 2 + half] = s;
+  } else if constexpr (EPI == EPI_DUAL) {
+    // 32x33 fp32 staging tile: transposes "thread == row" into "lane == column" so that every store instruction
+    // writes one contiguous 128-byte row segment
+    float inv_r, s0, sh, dust;
+    dual_row_setup(p, g, m, inv_r, s0, sh, dust);
+    for (int c = c_begin; c < c_end; ++c) {
+      if (n0 + c * 32 < p.n_valid) {
+        tmem_ld32(taddr + c * 32, v);
+        dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage, inv_r, s0, sh, dust);
+      }
+    }
+    release();
+  } else {
+    for (int c = c_begin; c < c_end; ++c) {
+      tmem_ld32(taddr + c * 32, v);
+      float4* dst = reinterpret_cast<float4*>(stage + lane * (W + 4) + (c - c_begin) * 32);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+    }
+    release();
+    __syncwarp();
+    epilogue_rows<EPI, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, 0.f, 0.f);
+  }
+}
+
 // ---- kernel ------------------------------------------------------------------------------------------
 template <int BN, int EPI, int GEMM_STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, (GEMM_STAGES <= 3) ? 2 : 1)
@@ -213,78 +288,153 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   __syncwarp();
 
-  // ===== epilogue: TMEM -> registers -> global, by ALL 8 warps =====
-  // warp w may read TMEM lanes 32*(w%4)..+31 (its quadrant); warps w and w+4 share a quadrant and split the
-  // tile's 32-column chunks between them.  The producer / MMA warps join once their loops have drained.
-  {
-    const int q = warp & 3;
-    const int half = warp >> 2;
-    constexpr int CHUNKS = BN / 32;
-    constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
-    const int c_begin = half * CPH;
-    const int c_end = (c_begin + CPH < CHUNKS) ? c_begin + CPH : CHUNKS;
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    pdl_trigger();               // main loop done: the next kernel's CTAs may start their prologue under our epilogue
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float v[32];
-    constexpr int W = BN / 2;                                  // columns owned by this warp
-    float* stage = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * (W + 4));
-    if constexpr (EPI == EPI_LN) {
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) {
-        tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum += v[j];
-      }
-      const float mean = sum * (1.0f / BN);
-      float sq = 0.f;
-#pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) {
-        tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq += d * d; }
-      }
-      const float rstd = rsqrtf(sq * (1.0f / BN) + p.eps);
-      for (int c = c_begin; c < c_end; ++c) {
-        tmem_ld32(taddr + c * 32, v);
-        float4* dst = reinterpret_cast<float4*>(stage + lane * (W + 4) + (c - c_begin) * 32);
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
-      }
-      __syncwarp();
-      epilogue_rows<EPI_LN, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, mean, rstd);
-    } else if constexpr (EPI == EPI_LSE) {
-      float s = 0.f;
-      for (int c = c_begin; c < c_end; ++c) {
-        tmem_ld32(taddr + c * 32, v);
-        s += lse_partial(p, g, n0 + c * 32, v);
-      }
-      if (m < p.n_valid) p.row_sum[((size_t)g * p.n_valid + m) * p.sum_slots + blockIdx.y * 2 + half] = s;
-    } else if constexpr (EPI == EPI_DUAL) {
-      // per-warp 32x33 fp32 staging tile in the (now idle) pipeline smem: transposes "thread == row" into
-      // "lane == column" so that every store instruction writes one contiguous 128-byte row segment
-      float* stage33 = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * 33);
-      float inv_r, s0, sh, dust;
-      dual_row_setup(p, g, m, inv_r, s0, sh, dust);
-      for (int c = c_begin; c < c_end; ++c) {
-        if (n0 + c * 32 < p.n_valid) {
-          tmem_ld32(taddr + c * 32, v);
-          dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage33, inv_r, s0, sh, dust);
+  // ===== epilogue: TMEM -> registers -> smem -> global, by ALL 8 warps =====
+  // The producer / MMA warps join once their loops have drained.
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  pdl_trigger();                 // main loop done: the next kernel's CTAs may start their prologue under our epilogue
+  tile_epilogue<BN, EPI>(p, g, m0, n0, (int)blockIdx.y, warp & 3, warp >> 2, lane, tmem_base,
+                         reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * (BN / 2 + 4)), [] {});
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---- persistent kernel ---------------------------------------------------------------------------------
+// For grids with more tiles than SMs: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so
+// neighbouring CTAs share the A tile in L2).  The smem ring never drains between tiles, and the accumulator is
+// double-buffered in TMEM (2 x BN columns) so that the MMA of tile i+1 runs under the epilogue of tile i:
+//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warp 3: idle | warps 4-11: epilogue
+constexpr int PERSIST_THREADS = 384;
+constexpr int PERSIST_STAGES = 4;
+
+template <int BN>
+constexpr int gemm_persistent_smem_bytes() {
+  return PERSIST_STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 8 * 32 * (BN / 2 + 4) * 4 + 1024 + 256;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const GemmParams p, const int tiles_m, const int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_BYTES = BN * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGING_BYTES = 8 * 32 * (BN / 2 + 4) * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t staging = base + PERSIST_STAGES * STAGE_BYTES;
+  const uint32_t bar_base = staging + STAGING_BYTES;
+  const uint32_t full_bar0 = bar_base;
+  const uint32_t empty_bar0 = bar_base + 8 * PERSIST_STAGES;
+  const uint32_t tfull_bar0 = bar_base + 16 * PERSIST_STAGES;        // [2]
+  const uint32_t tempty_bar0 = tfull_bar0 + 16;                      // [2]
+  const uint32_t tmem_ptr_addr = tempty_bar0 + 16;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_group = tiles_m * tiles_n;
+  const int total = tiles_per_group * p.groups;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < PERSIST_STAGES; ++s) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar0 + 8 * a, 1); mbar_init(tempty_bar0 + 8 * a, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer: the ring runs across tile boundaries =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int g = t / tiles_per_group, r = t - g * tiles_per_group;
+        const int m0 = (r / tiles_n) * BLOCK_M, n0 = (r % tiles_n) * BN;
+        const int a_col0 = p.a_col_base + g * p.a_col_group_off;
+        const int a_row0 = m0 + g * p.a_row_group_off;
+        const int b_row0 = n0 + g * p.b_row_group_off;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int tap = kc / p.chunks_per_tap;
+          const int kin = kc - tap * p.chunks_per_tap;
+          mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint32_t fb = full_bar0 + 8 * stage;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          tma_load_2d(sa, &tmA, fb, a_col0 + kin * BLOCK_K, a_row0 + p.tap_shift[tap]);
+          tma_load_2d(sa + A_BYTES, &tmB, fb, kc * BLOCK_K, b_row0);
+          if (++stage == PERSIST_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    } else {
-      for (int c = c_begin; c < c_end; ++c) {
-        tmem_ld32(taddr + c * 32, v);
-        float4* dst = reinterpret_cast<float4*>(stage + lane * (W + 4) + (c - c_begin) * 32);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator (it & 1) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    constexpr uint32_t idesc = umma_idesc_f16<BN>();
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(tempty_bar0 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * BN;
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(full_bar0 + 8 * stage, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar0 + 8 * stage);
+          if (kc == p.k_chunks - 1) umma_commit(tfull_bar0 + 8 * acc);
+        }
+        __syncwarp();
+        if (++stage == PERSIST_STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      epilogue_rows<EPI, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, 0.f, 0.f);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps =====
+    const int ew = warp - 4;
+    const int q = warp & 3, half = ew >> 2;
+    float* stage_buf = reinterpret_cast<float*>(smem_raw + (staging - raw)) + ew * (32 * (BN / 2 + 4));
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int g = t / tiles_per_group, r = t - g * tiles_per_group;
+      const int n_tile = r % tiles_n;
+      const int m0 = (r / tiles_n) * BLOCK_M, n0 = n_tile * BN;
+      const int acc = it & 1;
+      mbar_wait(tfull_bar0 + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tb = tempty_bar0 + 8 * acc;
+      tile_epilogue<BN, EPI>(p, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
+      });
+      __syncwarp();                       // staging block is reused by the next tile
     }
   }
 
@@ -292,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 

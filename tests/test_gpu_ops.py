@@ -33,6 +33,52 @@ def test_gemm_store_h_bias_gelu(impl, M, N, K):
     assert rel_err(out, ref) < 2e-3
 
 
+def test_persistent_gemm_large_grids():
+    """Grids with more tiles than SMs take the persistent kernel (several tiles per CTA, accumulator double-buffered
+    in TMEM): bias+GELU store, fp32 residual, grouped LayerNorm epilogue and a 3x3 conv, all against torch."""
+    M, N, K = 4000, 1536, 384                                   # 32 x 12 = 384 tiles
+    a, w, bias = _rand(M, K, seed=40).half(), _rand(N, K, scale=0.05, seed=41).half(), _rand(N, scale=0.1, seed=42)
+    out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+    gemm("STORE_H", a, w, M, N, K, bias=bias, act=1, out_h=out, out_h_ld=N)
+    assert rel_err(out, F.gelu(a.float() @ w.float().t() + bias)) < 2e-3
+    M, N, K = 9000, 768, 768                                    # 71 x 6 = 426 tiles, K = 12 chunks
+    a, w = _rand(M, K, seed=43).half(), _rand(N, K, scale=0.05, seed=44).half()
+    bias, gamma, x = _rand(N, scale=0.1, seed=45), _rand(N, seed=46), _rand(M, N, seed=47)
+    ref = x + gamma * (a.float() @ w.float().t() + bias)
+    gemm("RESID_F", a, w, M, N, K, bias=bias, gamma=gamma, out_f=x, out_f_ld=N)
+    assert rel_err(x, ref) < 1e-5
+    R, G, K = 9000, 4, 256                                      # 71 x 1 x 4 = 284 tiles
+    a, w = _rand(R, G * K, seed=48).half(), _rand(G * 128, K, scale=0.1, seed=49).half()
+    gamma, beta, x32 = _rand(G * 128, seed=50), _rand(G * 128, seed=51), _rand(R, G * 128, seed=52)
+    x_ref = x32.clone()
+    out_h = torch.zeros(R, G * 256, dtype=torch.float16, device=DEV)
+    gemm("LN", a, w, R, 128, K, groups=G, a_col_group_off=K, b_row_group_off=128, gamma=gamma, beta=beta, ln_group_off=128,
+         eps=1e-5, out_f=x32, out_f_ld=G * 128, out_f_group_off=128, out_h=out_h, out_h_ld=G * 256, out_h_group_off=256)
+    for g in range(G):
+        acc = a[:, g * K:(g + 1) * K].float() @ w[g * 128:(g + 1) * 128].float().t()
+        ref = x_ref[:, g * 128:(g + 1) * 128] + F.layer_norm(acc, (128,), gamma[g * 128:(g + 1) * 128], beta[g * 128:(g + 1) * 128], 1e-5)
+        assert rel_err(x32[:, g * 128:(g + 1) * 128], ref) < 1e-4, g
+        assert rel_err(out_h[:, g * 256:g * 256 + 128], ref) < 1e-3, g
+    n_img, gh, gw, cin, cout = 6, 51, 38, 128, 128              # 100 x 1 x 2 groups = 200 tiles
+    h2, w2, Gc = gh + 2, gw + 2, 2
+    xc = _rand(n_img, Gc * cin, gh, gw, seed=53).half()
+    wt = _rand(Gc * cout, cin, 3, 3, scale=0.05, seed=54).half()
+    xp = torch.zeros(n_img, h2, w2, Gc * cin, dtype=torch.float16, device=DEV)
+    xp[:, 1:-1, 1:-1] = xc.permute(0, 2, 3, 1)
+    wp = wt.permute(0, 2, 3, 1).reshape(Gc * cout, 9 * cin).contiguous()
+    Rr = n_img * h2 * w2
+    o32 = torch.full((Rr, Gc * cout), 7.0, device=DEV)
+    taps = [(ky - 1) * w2 + (kx - 1) for ky in range(3) for kx in range(3)]
+    gemm("CONV", xp.reshape(Rr, Gc * cin), wp, Rr, cout, taps=taps, chunks_per_tap=cin // 64, groups=Gc, a_col_group_off=cin,
+         b_row_group_off=cout, act=2, pad_h2=h2, pad_w2=w2, out_f=o32, out_f_ld=Gc * cout, out_f_group_off=cout)
+    got = o32.reshape(n_img, h2, w2, Gc * cout)
+    for g in range(Gc):
+        ref = F.relu(F.conv2d(xc[:, g * cin:(g + 1) * cin].float(), wt[g * cout:(g + 1) * cout].float(), padding=1))
+        assert rel_err(got[:, 1:-1, 1:-1, g * cout:(g + 1) * cout].permute(0, 3, 1, 2), ref) < 1e-5, g
+    ring = got.clone(); ring[:, 1:-1, 1:-1] = 0
+    assert float(ring.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_gemm_resid_layerscale(impl):
     M, N, K = 515, 384, 384
@@ -186,10 +232,11 @@ def test_linear_attention():
         assert rel_err(got, ref) < 2e-3, g
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
-def test_matcher_epilogues_vs_dual_softmax(impl):
-    """LSE x2 + DUAL epilogues on split-fp16 descriptors == softmax(dim1)*softmax(dim2) with dustbin."""
-    B, N, T = 2, 300, 0.1
+@pytest.mark.parametrize("impl,B,N", [("simt", 2, 300), ("tc", 2, 300), ("tc", 1, 1938)])
+def test_matcher_epilogues_vs_dual_softmax(impl, B, N):
+    """LSE x2 + DUAL epilogues on split-fp16 descriptors == softmax(dim1)*softmax(dim2) with dustbin
+    (N = 1938: the full BASELINE size, 256 tiles -> persistent kernel)."""
+    T = 0.1
     d0 = F.normalize(_rand(B, N, 128, seed=31), dim=-1)
     d1 = F.normalize(_rand(B, N, 128, seed=32), dim=-1)
     s0, s1 = torch.rand(B, N, device=DEV), torch.rand(B, N, device=DEV)
