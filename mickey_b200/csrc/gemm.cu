@@ -195,6 +195,12 @@ static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return MK_OK;
 }
 
+static bool wide_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_WIDE"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  return v == 1;
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -244,8 +250,19 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
     // tile (K >= 768) or there are many tiles per SM.  Measured on B200: +29 % on the ViT-B GEMMs of the B=32
     // workload (523 -> 674 TFLOP/s), 1.13 PFLOP/s on a 16384x4096x4096 GEMM; but for the K=384, ~2-tiles-per-SM GEMMs
     // of the B=1 workload the two co-resident one-tile CTAs (16 epilogue warps per SM instead of 8) are faster.
-    if (persistent_enabled() && (p.k_chunks >= 12 || ctas >= 4LL * sm_count()))
+    if (persistent_enabled() && (p.k_chunks >= 12 || ctas >= 4LL * sm_count())) {
+      // 128 x 256 tiles (one N=256 UMMA per K step, A tile re-read half as often: 85 instead of 64 flop per byte of
+      // L2 traffic, which is what bounds the 128 x 128 tiling) when N allows and enough tiles remain
+      if constexpr (BN == 128 && (EPI == EPI_STORE_H || EPI == EPI_RESID_F || EPI == EPI_CONV || EPI == EPI_STORE_F)) {
+        if (wide_enabled() && p.N % 256 == 0 && ctas / 2 >= 2LL * sm_count()) {
+          CUtensorMap tmB2;
+          rc = make_tensor_map_f16(&tmB2, B.ptr, B.rows, B.cols, B.ld, 256);
+          if (rc) return rc;
+          return launch_persistent<256, EPI>(dim3(grid.x, grid.y / 2, grid.z), tmA, tmB2, p, stream);
+        }
+      }
       return launch_persistent<BN, EPI>(grid, tmA, tmB, p, stream);
+    }
     return launch_tc<BN, EPI, 3>(grid, tmA, tmB, p, stream);
   }
   MK_CUDA_CHECK(cudaGetLastError());

@@ -182,15 +182,22 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0
     }
     release();
   } else {
-    for (int c = c_begin; c < c_end; ++c) {
-      tmem_ld32(taddr + c * 32, v);
-      float4* dst = reinterpret_cast<float4*>(stage + lane * (W + 4) + (c - c_begin) * 32);
+    // the warp's columns are processed in passes of at most 64 (two 32-column TMEM loads) through the staging block
+    constexpr int PW = (W > 64) ? 64 : W;                 // staged columns per pass
+    constexpr int PCH = PW / 32;                          // chunks per pass
+    for (int c0 = c_begin; c0 < c_end; c0 += PCH) {
 #pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+      for (int cc = 0; cc < PCH; ++cc) {
+        tmem_ld32(taddr + (c0 + cc) * 32, v);
+        float4* dst = reinterpret_cast<float4*>(stage + lane * (PW + 4) + cc * 32);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+      }
+      if (c0 + PCH >= c_end) release();                   // accumulator fully read
+      __syncwarp();
+      epilogue_rows<EPI, PW>(p, g, m0 + q * 32, lane, n0 + c0 * 32, stage, 0.f, 0.f);
+      __syncwarp();
     }
-    release();
-    __syncwarp();
-    epilogue_rows<EPI, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, 0.f, 0.f);
   }
 }
 
@@ -310,11 +317,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // double-buffered in TMEM (2 x BN columns) so that the MMA of tile i+1 runs under the epilogue of tile i:
 //   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warp 3: idle | warps 4-11: epilogue
 constexpr int PERSIST_THREADS = 384;
-constexpr int PERSIST_STAGES = 4;
+template <int BN> constexpr int persist_stages() { return BN >= 256 ? 3 : 4; }      // 3 x 48 KB or 4 x 32 KB
+template <int BN> constexpr int staged_cols() { return (BN / 2 > 64) ? 64 : BN / 2; }
 
 template <int BN>
 constexpr int gemm_persistent_smem_bytes() {
-  return PERSIST_STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 8 * 32 * (BN / 2 + 4) * 4 + 1024 + 256;
+  return persist_stages<BN>() * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 8 * 32 * (staged_cols<BN>() + 4) * 4 + 1024 + 256;
 }
 
 template <int BN, int EPI>
@@ -325,7 +333,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGING_BYTES = 8 * 32 * (BN / 2 + 4) * 4;
+  constexpr int PERSIST_STAGES = persist_stages<BN>();
+  constexpr int STAGING_BYTES = 8 * 32 * (staged_cols<BN>() + 4) * 4;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   const uint32_t raw = smem_u32(smem_raw);
@@ -419,7 +428,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // ===== epilogue warps =====
     const int ew = warp - 4;
     const int q = warp & 3, half = ew >> 2;
-    float* stage_buf = reinterpret_cast<float*>(smem_raw + (staging - raw)) + ew * (32 * (BN / 2 + 4));
+    float* stage_buf = reinterpret_cast<float*>(smem_raw + (staging - raw)) + ew * (32 * (staged_cols<BN>() + 4));
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int g = t / tiles_per_group, r = t - g * tiles_per_group;

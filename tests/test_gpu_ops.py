@@ -36,18 +36,26 @@ def test_gemm_store_h_bias_gelu(impl, M, N, K):
 def test_persistent_gemm_large_grids():
     """Grids with more tiles than SMs take the persistent kernel (several tiles per CTA, accumulator double-buffered
     in TMEM): bias+GELU store, fp32 residual, grouped LayerNorm epilogue and a 3x3 conv, all against torch."""
-    M, N, K = 4000, 1536, 384                                   # 32 x 12 = 384 tiles
-    a, w, bias = _rand(M, K, seed=40).half(), _rand(N, K, scale=0.05, seed=41).half(), _rand(N, scale=0.1, seed=42)
-    out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
-    gemm("STORE_H", a, w, M, N, K, bias=bias, act=1, out_h=out, out_h_ld=N)
-    assert rel_err(out, F.gelu(a.float() @ w.float().t() + bias)) < 2e-3
+    for M, N, K in ((4000, 1536, 384),      # 384 one-tile CTAs
+                    (20000, 1536, 768),     # 157 x 12 tiles, K = 12 chunks: persistent, 128 x 256 tiles
+                    (9000, 640, 1536)):     # N % 256 != 0: persistent, 128 x 128 tiles
+        a, w, bias = _rand(M, K, seed=40).half(), _rand(N, K, scale=0.05, seed=41).half(), _rand(N, scale=0.1, seed=42)
+        out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+        gemm("STORE_H", a, w, M, N, K, bias=bias, act=1, out_h=out, out_h_ld=N)
+        assert rel_err(out, F.gelu(a.float() @ w.float().t() + bias)) < 2e-3, (M, N, K)
+    M, N, K = 30000, 768, 768                                   # 235 x 6 tiles -> 128 x 256 tiles, fp32 residual
+    a, w = _rand(M, K, seed=43).half(), _rand(N, K, scale=0.05, seed=44).half()
+    bias, gamma, x = _rand(N, scale=0.1, seed=45), _rand(N, seed=46), _rand(M, N, seed=47)
+    ref = x + gamma * (a.float() @ w.float().t() + bias)
+    gemm("RESID_F", a, w, M, N, K, bias=bias, gamma=gamma, out_f=x, out_f_ld=N)
+    assert rel_err(x, ref) < 1e-5
     M, N, K = 9000, 768, 768                                    # 71 x 6 = 426 tiles, K = 12 chunks
     a, w = _rand(M, K, seed=43).half(), _rand(N, K, scale=0.05, seed=44).half()
     bias, gamma, x = _rand(N, scale=0.1, seed=45), _rand(N, seed=46), _rand(M, N, seed=47)
     ref = x + gamma * (a.float() @ w.float().t() + bias)
     gemm("RESID_F", a, w, M, N, K, bias=bias, gamma=gamma, out_f=x, out_f_ld=N)
     assert rel_err(x, ref) < 1e-5
-    R, G, K = 9000, 4, 256                                      # 71 x 1 x 4 = 284 tiles
+    R, G, K = 80000, 4, 256                                     # 625 x 1 x 4 = 2500 tiles -> persistent LayerNorm epilogue
     a, w = _rand(R, G * K, seed=48).half(), _rand(G * 128, K, scale=0.1, seed=49).half()
     gamma, beta, x32 = _rand(G * 128, seed=50), _rand(G * 128, seed=51), _rand(R, G * 128, seed=52)
     x_ref = x32.clone()
@@ -59,8 +67,12 @@ def test_persistent_gemm_large_grids():
         ref = x_ref[:, g * 128:(g + 1) * 128] + F.layer_norm(acc, (128,), gamma[g * 128:(g + 1) * 128], beta[g * 128:(g + 1) * 128], 1e-5)
         assert rel_err(x32[:, g * 128:(g + 1) * 128], ref) < 1e-4, g
         assert rel_err(out_h[:, g * 256:g * 256 + 128], ref) < 1e-3, g
-    n_img, gh, gw, cin, cout = 6, 51, 38, 128, 128              # 100 x 1 x 2 groups = 200 tiles
-    h2, w2, Gc = gh + 2, gw + 2, 2
+    _conv_case(6, 51, 38, 128, 128, 2)                          # 100 x 1 x 2 groups, 128-wide tiles
+    _conv_case(16, 51, 38, 128, 256, 2)                         # 265 x 2 x 2 groups -> 128 x 256 tiles
+
+
+def _conv_case(n_img, gh, gw, cin, cout, Gc):
+    h2, w2 = gh + 2, gw + 2
     xc = _rand(n_img, Gc * cin, gh, gw, seed=53).half()
     wt = _rand(Gc * cout, cin, 3, 3, scale=0.05, seed=54).half()
     xp = torch.zeros(n_img, h2, w2, Gc * cin, dtype=torch.float16, device=DEV)
@@ -232,10 +244,10 @@ def test_linear_attention():
         assert rel_err(got, ref) < 2e-3, g
 
 
-@pytest.mark.parametrize("impl,B,N", [("simt", 2, 300), ("tc", 2, 300), ("tc", 1, 1938)])
+@pytest.mark.parametrize("impl,B,N", [("simt", 2, 300), ("tc", 2, 300), ("tc", 1, 1938), ("tc", 3, 1938)])
 def test_matcher_epilogues_vs_dual_softmax(impl, B, N):
     """LSE x2 + DUAL epilogues on split-fp16 descriptors == softmax(dim1)*softmax(dim2) with dustbin
-    (N = 1938: the full BASELINE size, 256 tiles -> persistent kernel)."""
+    (N = 1938: the full BASELINE size; B = 3 gives 768 tiles -> persistent kernel)."""
     T = 0.1
     d0 = F.normalize(_rand(B, N, 128, seed=31), dim=-1)
     d1 = F.normalize(_rand(B, N, 128, seed=32), dim=-1)
