@@ -176,6 +176,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
                                               const float* __restrict__ stage, float mean_l, float rstd_l) {
   constexpr int CPL = W / 32;
   constexpr int LDS = W + 4;
+  constexpr int RB = 8;                  // rows per batch: all global loads of a batch are issued before any store
   const int col = col_base + lane * CPL;
   float bias[CPL], gam[CPL], bet[CPL];
 #pragma unroll
@@ -184,6 +185,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
   if constexpr (EPI == EPI_RESID_F) { ldg_f<CPL>(p.bias + col, bias); ldg_f<CPL>(p.gamma + col, gam); }
   if constexpr (EPI == EPI_LN) { ldg_f<CPL>(p.gamma + (size_t)g * p.ln_group_off + col, gam); ldg_f<CPL>(p.beta + (size_t)g * p.ln_group_off + col, bet); }
   const bool use_aux = (EPI == EPI_CONV) && p.aux && ((p.aux_group_mask >> g) & 1);
+  const bool use_res = (EPI == EPI_CONV) && p.res_h;
+  const bool ln_res = (EPI == EPI_LN) && p.out_f;
   const int rows = min(32, p.M - row0);
   // per-row index math is done once by lane r (for row r) and broadcast with a shuffle inside the loop
   int my_pos = 0, my_valid = 1, my_orow = 0;
@@ -198,76 +201,73 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
       my_orow = img * (p.tok_per_img + 1) + 1 + my_pos;  // row of the token matrix (cls rows skipped)
     }
   }
-#pragma unroll 4                                  // 4 rows in flight per lane: independent chains for ILP
-  for (int r = 0; r < rows; ++r) {
-    const int m = row0 + r;
-    float v[CPL];
-    ld_f<CPL>(stage + r * LDS + lane * CPL, v);
-    if constexpr (EPI == EPI_STORE_H) {
+  for (int r0 = 0; r0 < rows; r0 += RB) {
+    float v[RB][CPL], x[RB][CPL], a[RB][CPL];
+    int pos[RB], orow[RB];
+    bool valid[RB];
+    // ---- phase 1: staged accumulators + every global operand of the batch (independent loads in flight)
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        v[i] += bias[i];
-        v[i] = (p.act == ACT_GELU) ? gelu_erf(v[i]) : ((p.act == ACT_RELU) ? fmaxf(v[i], 0.f) : v[i]);
+    for (int i = 0; i < RB; ++i) {
+      const int r = r0 + i;                              // r < 32 always; rows beyond `rows` are loaded from smem only
+      const int m = row0 + r;
+      const bool live = r < rows;
+      ld_f<CPL>(stage + r * LDS + lane * CPL, v[i]);
+      pos[i] = __shfl_sync(0xffffffffu, my_pos, r);
+      orow[i] = __shfl_sync(0xffffffffu, my_orow, r);
+      valid[i] = __shfl_sync(0xffffffffu, my_valid, r) != 0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { x[i][k] = 0.f; a[i][k] = 0.f; }
+      if (live) {
+        if constexpr (EPI == EPI_RESID_F) ld_f<CPL>(p.out_f + (size_t)m * p.out_f_ld + col, x[i]);
+        if constexpr (EPI == EPI_PATCH) ldg_f<CPL>(p.aux + (size_t)pos[i] * p.N + col, a[i]);
+        if constexpr (EPI == EPI_CONV) {
+          if (use_res) ld_h<CPL>(p.res_h + (size_t)g * p.res_h_group_off + (size_t)m * p.res_h_ld + col, x[i]);
+          if (use_aux) ldg_f<CPL>(p.aux + (size_t)pos[i] * p.N + col, a[i]);
+        }
+        if constexpr (EPI == EPI_LN) { if (ln_res) ld_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, x[i]); }
       }
-      st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v);
-    } else if constexpr (EPI == EPI_RESID_F) {
-      float* o = p.out_f + (size_t)m * p.out_f_ld + col;
-      float x[CPL];
-      ld_f<CPL>(o, x);
+    }
+    // ---- phase 2: arithmetic + stores
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) x[i] = fmaf(gam[i], v[i] + bias[i], x[i]);
-      st_f<CPL>(o, x);
-    } else if constexpr (EPI == EPI_PATCH) {
-      const int tk = __shfl_sync(0xffffffffu, my_pos, r), orow = __shfl_sync(0xffffffffu, my_orow, r);
-      float a[CPL];
-      ldg_f<CPL>(p.aux + (size_t)tk * p.N + col, a);
+    for (int i = 0; i < RB; ++i) {
+      const int r = r0 + i;
+      const int m = row0 + r;
+      if (r >= rows) continue;
+      if constexpr (EPI == EPI_STORE_H) {
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) v[i] += a[i];
-      st_f<CPL>(p.out_f + (size_t)orow * p.out_f_ld + col, v);
-    } else if constexpr (EPI == EPI_CONV) {
-      const int pos = __shfl_sync(0xffffffffu, my_pos, r);
-      const bool valid = __shfl_sync(0xffffffffu, my_valid, r) != 0;
+        for (int k = 0; k < CPL; ++k) {
+          float t = v[i][k] + bias[k];
+          v[i][k] = (p.act == ACT_GELU) ? gelu_erf(t) : ((p.act == ACT_RELU) ? fmaxf(t, 0.f) : t);
+        }
+        st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v[i]);
+      } else if constexpr (EPI == EPI_RESID_F) {
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) v[i] += bias[i];
-      if (p.res_h) {
-        float rr[CPL];
-        ld_h<CPL>(p.res_h + (size_t)g * p.res_h_group_off + (size_t)m * p.res_h_ld + col, rr);
+        for (int k = 0; k < CPL; ++k) x[i][k] = fmaf(gam[k], v[i][k] + bias[k], x[i][k]);
+        st_f<CPL>(p.out_f + (size_t)m * p.out_f_ld + col, x[i]);
+      } else if constexpr (EPI == EPI_PATCH) {
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] += rr[i];
+        for (int k = 0; k < CPL; ++k) v[i][k] += a[i][k];
+        st_f<CPL>(p.out_f + (size_t)orow[i] * p.out_f_ld + col, v[i]);
+      } else if constexpr (EPI == EPI_CONV) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          float t = apply_act(v[i][k] + bias[k] + x[i][k], p.act) + a[i][k];
+          v[i][k] = valid[i] ? t : 0.f;
+        }
+        if (p.out_f) st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v[i]);
+        if (p.out_h) st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v[i]);
+      } else if constexpr (EPI == EPI_STORE_F) {
+        st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v[i]);
+      } else if constexpr (EPI == EPI_LN) {
+        const float mean = __shfl_sync(0xffffffffu, mean_l, r), rstd = __shfl_sync(0xffffffffu, rstd_l, r);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          float t = (v[i][k] - mean) * rstd * gam[k] + bet[k] + x[i][k];
+          v[i][k] = valid[i] ? t : 0.f;
+        }
+        if (ln_res) st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v[i]);
+        st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v[i]);
       }
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) v[i] = apply_act(v[i], p.act);
-      if (use_aux) {
-        float a[CPL];
-        ldg_f<CPL>(p.aux + (size_t)pos * p.N + col, a);
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] += a[i];
-      }
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] = 0.f;
-      }
-      if (p.out_f) st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v);
-      if (p.out_h) st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v);
-    } else if constexpr (EPI == EPI_STORE_F) {
-      st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v);
-    } else if constexpr (EPI == EPI_LN) {
-      const float mean = __shfl_sync(0xffffffffu, mean_l, r), rstd = __shfl_sync(0xffffffffu, rstd_l, r);
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) v[i] = (v[i] - mean) * rstd * gam[i] + bet[i];
-      float* o = p.out_f ? p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col : nullptr;
-      if (o) {
-        float x[CPL];
-        ld_f<CPL>(o, x);
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] += x[i];
-      }
-      if (__shfl_sync(0xffffffffu, my_valid, r) == 0) {
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] = 0.f;
-      }
-      if (o) st_f<CPL>(o, v);
-      st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v);
     }
   }
 }
