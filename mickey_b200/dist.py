@@ -43,19 +43,43 @@ def unpack_pose(packed: torch.Tensor):
     return packed[:, :9].reshape(B, 3, 3), packed[:, 9:12].reshape(B, 1, 3), packed[:, 12:13]
 
 
-def gather_poses(packed: torch.Tensor) -> torch.Tensor:
-    """All-gather of [B_local, 13] -> [B_global, 13] in rank order (equal B_local on every rank)."""
+def gather_poses(packed: torch.Tensor, n_pairs: int = None) -> torch.Tensor:
+    """All-gather of [B_local, 13] -> [B_global, 13] in rank order -- still ONE collective.  With `n_pairs` (the
+    global batch) the shards may be ragged (shard_range spreads the remainder over the first ranks): every rank
+    pads its block to ceil(n_pairs / world) rows and the padding rows are dropped after the gather.  Without it
+    every rank must hold the same number of pairs."""
     rank, ws = world()
     if ws == 1:
         return packed
-    out = torch.empty(ws * packed.shape[0], packed.shape[1], dtype=packed.dtype, device=packed.device)
-    dist.all_gather_into_tensor(out, packed.contiguous())
-    return out
+    packed = packed.contiguous()
+    if n_pairs is None:
+        out = torch.empty(ws * packed.shape[0], packed.shape[1], dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(out, packed)
+        return out
+    rows = -(-n_pairs // ws)
+    block = packed
+    if packed.shape[0] != rows:
+        block = packed.new_zeros(rows, packed.shape[1])
+        block[:packed.shape[0]] = packed
+    out = torch.empty(ws * rows, packed.shape[1], dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, block)
+    if n_pairs == ws * rows:
+        return out
+    keep = [out[r * rows:r * rows + (e - s)] for r in range(ws) for s, e in [shard_range(n_pairs, r, ws)]]
+    return torch.cat(keep, dim=0)
 
 
 def forward_sharded(model, data: dict, return_inliers: bool = False):
     """Run `model` on this rank's shard of a global batch and return the globally gathered (R, t, inliers)."""
     local = shard_batch(data)
-    R, t = model(local, return_inliers=return_inliers)
-    allp = gather_poses(pack_pose(R, t, local["inliers"]))
-    return unpack_pose(allp)
+    n = data["image0"].shape[0]
+    if local["image0"].shape[0] == 0:
+        # more ranks than pairs: this rank contributes an empty block (it still joins the collective)
+        dev = data["image0"].device
+        if dist.get_backend() == "nccl" and dev.type != "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        mine = torch.zeros(0, 13, dtype=torch.float32, device=dev)
+    else:
+        R, t = model(local, return_inliers=return_inliers)
+        mine = pack_pose(R, t, local["inliers"])
+    return unpack_pose(gather_poses(mine, n_pairs=n))

@@ -3,6 +3,7 @@ all-gather of packed poses.  The model is replaced by a deterministic stand-in (
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -62,8 +63,9 @@ def test_pack_unpack_roundtrip():
     assert torch.equal(R, R2) and torch.equal(t, t2) and torch.equal(i, i2)
 
 
-def test_two_rank_gloo_gather_matches_single_process(tmp_path):
-    n_pairs, world = 6, 2
+@pytest.mark.parametrize("n_pairs", [6, 5, 1])
+def test_two_rank_gloo_gather_matches_single_process(tmp_path, n_pairs):
+    world = 2
     out = str(tmp_path / "r0.pt")
     mp.spawn(_worker, args=(world, _free_port(), n_pairs, out), nprocs=world, join=True)
     got = torch.load(out)
