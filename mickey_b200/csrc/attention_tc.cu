@@ -2,18 +2,25 @@
 //
 //   out[img, q, head] = softmax(q k^T / 8) v          head_dim 64, T tokens per image (1939 at 720x540)
 //
-// CTA = 128 queries of one (image, head); KV is streamed in 128-key tiles.  192 threads:
-//   warps 0-3 : softmax + correction + epilogue; warp w owns TMEM lanes 32w..32w+31, thread == query row
-//   warp 4    : TMA producer (Q once; K and V rings, 2 stages each, 16 KB tiles, 128-byte swizzle)
-//   warp 5    : TMEM allocator + single-thread MMA issuer
+// CTA = 128 queries of one (image, head); KV is streamed in 128-key tiles.  320 threads:
+//   warps 0-7 : softmax + correction + epilogue.  Warp w owns TMEM lanes 32(w&3)..+31 (thread == query row) and the
+//               key half w>>2 of every tile (64 of the 128 S columns), so a row is shared by two threads
+//   warp 8    : TMA producer (Q once; K and V rings, 2 stages each, 16 KB tiles, 128-byte swizzle)
+//   warp 9    : TMEM allocator + single-thread MMA issuer
 // TMEM (256 columns, two CTAs per SM):
 //   [0,128)   S = Q K^T, fp32             (tcgen05.mma SS, both operands K-major)
 //   [128,192) P = exp2(S - m), fp16 x2    (written by the softmax threads with tcgen05.st, read as the A operand)
 //   [192,256) O += P V, fp32              (tcgen05.mma TS, B = V tile as an MN-major operand)
 // Softmax is "online" with lazy rescaling: the running reference max m_ref only moves when the tile max exceeds
 // it by more than 8 (log2 units), so O in TMEM is rescaled rarely and P stays below 2^8 in fp16.  QK^T of tile
-// j+1 is issued as soon as the softmax warps have pulled S_j into registers, so it overlaps their exp work; the
-// second resident CTA fills the remaining bubbles.
+// j+1 is issued as soon as the softmax warps have pulled S_j into registers, so it overlaps their exp work.
+//
+// Why two threads per row: with head_dim 64 the kernel is bound by MUFU.EX2 (16/clk/SM: 1024 clocks per 128x128
+// tile against 512 for its two MMAs).  Per tile a softmax warp alternates that MUFU phase with ~900 clocks of TMEM
+// traffic, max and barrier latency, so the sub-partition's MUFU idles unless other warps are in their exp phase.
+// With one thread per row (2 warps per sub-partition at 2 CTAs/SM) clock stamps showed 3200 clocks per tile pair
+// (MUFU 67 % busy, the older CTA winning arbitration); splitting the columns gives 4 half-size warps per
+// sub-partition, enough independent phases to keep the MUFU fed (profiles/r01_notes.md).
 #include "gemm_tc.cuh"
 #include "ops.h"
 #include "gemm.h"
@@ -22,9 +29,11 @@
 
 namespace mk {
 
-constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64, FA_THREADS = 192, FA_KV_STAGES = 2;
+constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64, FA_THREADS = 320, FA_KV_STAGES = 2;
+constexpr int FA_SOFTMAX_WARPS = 8, FA_WARP_TMA = 8, FA_WARP_MMA = 9;
 constexpr int FA_TILE_BYTES = 128 * 128;                                   // 128 rows x 64 fp16
-constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_KV_STAGES) + 1024 + 256;
+constexpr int FA_XCHG_BYTES = 2 * 2 * 128 * 4;                              // [tile parity][key half][row] floats
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_KV_STAGES) + 1024 + 256 + FA_XCHG_BYTES;
 constexpr uint32_t FA_COL_S = 0, FA_COL_P = 128, FA_COL_O = 192, FA_TMEM_COLS = 256;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -82,23 +91,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
   const uint32_t q_full = bars, k_full = bars + 8, k_empty = bars + 24, v_full = bars + 40, v_empty = bars + 56;
   const uint32_t s_full = bars + 72, s_empty = bars + 80, p_full = bars + 88, pv_done = bars + 96, tmem_slot = bars + 104;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* xchg = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, im = blockIdx.z;
   const int n_tiles = (T + FA_BK - 1) / FA_BK;
   const int row_base = im * T;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == FA_WARP_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
     mbar_init(q_full, 1);
     for (int s = 0; s < FA_KV_STAGES; ++s) {
       mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
       mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
     }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, FA_SOFTMAX_WARPS); mbar_init(p_full, FA_SOFTMAX_WARPS); mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == FA_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(FA_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -108,7 +118,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
   const uint32_t tmem_base = *tmem_ptr_gen;
   pdl_wait();
 
-  if (warp == 4) {
+  if (warp == FA_WARP_TMA) {
     // ===== TMA producer =====
     if (elect_one()) {
       mbar_expect_tx(q_full, FA_TILE_BYTES);
@@ -124,7 +134,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
         tma_load_2d(sV + st * FA_TILE_BYTES, &tmQKV, v_full + 8 * st, 2 * D + head * FA_D, row_base + j * FA_BK);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == FA_WARP_MMA) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FA_BK >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
     constexpr uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
@@ -168,17 +178,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
     }
   } else {
     // ===== softmax / correction / epilogue warps =====
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + FA_COL_S, tP = tmem_base + lane_off + FA_COL_P, tO = tmem_base + lane_off + FA_COL_O;
+    const int quad = warp & 3, half = warp >> 2;            // TMEM lane quadrant, key half of every tile
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + FA_COL_S + 64 * half;
+    const uint32_t tP = tmem_base + lane_off + FA_COL_P + 32 * half;
+    const uint32_t tO = tmem_base + lane_off + FA_COL_O + 32 * half;
+    const uint32_t pair_bar = 1 + quad;                     // named barrier of the two warps that share these rows
     float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float s[128];
+      float s[64];
       {
         float v[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           tmem_ld32(tS + c * 32, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) s[c * 32 + i] = v[i];
@@ -187,79 +202,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);         // S buffer may be overwritten by QK^T of the next tile
-      const int valid = T - j * FA_BK;             // keys of this tile that exist (>= 1)
-      if (valid < FA_BK) {                         // only the last tile has a key tail (warp-uniform branch)
+      const int valid = T - j * FA_BK - 64 * half; // keys of this half tile that exist (may be <= 0 in the last tile)
+      if (valid < 64) {                            // warp-uniform branch
 #pragma unroll
-        for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : -INFINITY;
+        for (int i = 0; i < 64; ++i) s[i] = (i < valid) ? s[i] : -INFINITY;
       }
-      // max of the RAW logits (scale_log2 > 0 commutes with max); 8 independent chains instead of one 128-long one
+      // max of the RAW logits (scale_log2 > 0 commutes with max); 8 independent chains instead of one 64-long one
       float mxa[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) mxa[k] = s[k];
 #pragma unroll
-      for (int i = 8; i < 128; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[i]);
+      for (int i = 8; i < 64; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[i]);
       float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-      mx *= scale_log2;
+      // row max over both key halves: exchange through shared memory (double-buffered by tile parity, so the next
+      // tile's write cannot overtake the partner's read), one 64-thread named barrier per tile
+      float* xm = xchg + (j & 1) * 256;
+      xm[half * 128 + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, xm[(half ^ 1) * 128 + row]) * scale_log2;   // finite: the tile holds at least one key
       float alpha = 1.0f;
-      const bool move = (mx > m_ref + 8.0f);       // always true for j == 0 (m_ref = -inf)
+      const bool move = (mx > m_ref + 8.0f);       // always true for j == 0 (m_ref = -inf); identical in both halves
       if (move) { alpha = ex2_approx(m_ref - mx); m_ref = mx; }
-      // p = 2^(s*scale - m_ref): one FFMA + one MUFU.EX2 per element, 8 partial sums for ILP
-      float sa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      // p = 2^(s*scale - m_ref): one FFMA + one MUFU.EX2 per element, 4 partial sums for ILP
+      float sa[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_ref;
-      uint32_t pk[64];
+      uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
+      for (int i = 0; i < 32; ++i) {
         const float p0 = ex2_approx(fmaf(s[2 * i], scale_log2, neg_m)), p1 = ex2_approx(fmaf(s[2 * i + 1], scale_log2, neg_m));
-        sa[(2 * i) & 7] += p0; sa[(2 * i + 1) & 7] += p1;
+        sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1;
         __half2 h = __floats2half2_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&h);
       }
-      const float sum = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
-      l_run = l_run * alpha + sum;
+      l_run = l_run * alpha + ((sa[0] + sa[1]) + (sa[2] + sa[3]));     // this thread's key half only
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);           // P buffer free, O quiescent
         tc_fence_after();
-        if (__any_sync(0xffffffffu, move)) {       // rescale this warp's 32 rows of O (alpha == 1 where unchanged)
+        if (__any_sync(0xffffffffu, move)) {       // rescale this warp's 32 rows x 32 columns of O (alpha == 1 where unchanged)
           float o[32];
+          tmem_ld32(tO, o);
+          uint32_t ob[32];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(tO + c * 32, o);
-            uint32_t ob[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(o[i] * alpha);
-            tmem_st32(tO + c * 32, ob);
-          }
+          for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(o[i] * alpha);
+          tmem_st32(tO, ob);
         }
       }
-      {
-        uint32_t half_pk[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) half_pk[i] = pk[c * 32 + i];
-          tmem_st32(tP + c * 32, half_pk);
-        }
-      }
+      tmem_st32(tP, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l -> fp16
+    // epilogue: O / (l of both key halves) -> fp16; this warp stores 32 of the head's 64 columns
+    float* xl = xchg + (n_tiles & 1) * 256;        // the parity the last tile did not use
+    xl[half * 128 + row] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float inv = 1.0f / (l_run + xl[(half ^ 1) * 128 + row]);
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc_fence_after();
     pdl_trigger();
-    const int q = q0 + warp * 32 + lane;
-    const float inv = 1.0f / l_run;
-    __half* dst = out + ((long long)(row_base + q)) * D + head * FA_D;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    const int q = q0 + row;
+    __half* dst = out + ((long long)(row_base + q)) * D + head * FA_D + 32 * half;
+    {
       float o[32];
-      tmem_ld32(tO + c * 32, o);
+      tmem_ld32(tO, o);
       if (q < T) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] *= inv;
-        store_h32(dst + c * 32, o);
+        store_h32(dst, o);
       }
     }
   }
@@ -267,7 +277,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 5) {
+  if (warp == FA_WARP_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FA_TMEM_COLS) : "memory");
   }
 }

@@ -33,151 +33,251 @@ struct Philox {
 };
 
 // Exp(1) variate with full relative precision near 0 (small E decides the race): E = -log1p(-u), u in (0,1)
-__device__ __forceinline__ float exp1_from_bits(uint32_t x) {
-  const float u = fminf(((float)x + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
+__device__ __forceinline__ float exp1_from_u(float u) {
+  u = fminf(u, 0.99999994f);
   return (u < 0.01f) ? u * (1.0f + u * (0.5f + u * (0.33333334f + 0.25f * u))) : -__logf(1.0f - u);
 }
 __device__ __forceinline__ float u01_from_bits(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f; }
 
-__device__ __forceinline__ uint32_t race_key(float p, uint32_t bits) {
-  return (p > 0.f) ? __float_as_uint(__fdividef(p, exp1_from_bits(bits))) : 0u;
+// 48-bit uniform of one (cell, stream): a 16-bit prefix (8 streams share one Philox call) refined by 32 more bits
+// that are only generated for the few cells whose prefix does not already rule them out.
+__device__ __forceinline__ float u_from_prefix(uint32_t prefix16, uint32_t low32) {
+  return ((float)prefix16 + ((float)low32 + 0.5f) * 2.3283064365386963e-10f) * 1.52587890625e-5f;
 }
+__device__ __forceinline__ uint32_t race_key(float p, float u) { return __float_as_uint(__fdividef(p, exp1_from_u(u))); }
 
-constexpr int HBINS = 2048;          // key >> 20 (sign is always 0)
+constexpr int HBINS = 2048;          // float bits >> 20 (sign is always 0): 8 exponent + 3 mantissa bits
 constexpr int SAMP_THREADS = 256;
-constexpr int SAMP_ELEMS_PER_BLOCK = 256 * 32;
+constexpr int SAMP_ELEMS_PER_BLOCK = 256 * 16;
+constexpr uint32_t PHILOX_TAG_PREFIX = 0x5bd1e995u, PHILOX_TAG_LOW = 0x2545F491u;
 
-// ---- pass A: histogram ------------------------------------------------------------------------------------
-// grid (blocks over N*N, ceil(IM/4), B); one Philox call per cell yields the noise of 4 streams.
-__global__ void __launch_bounds__(SAMP_THREADS)
-sampler_hist_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
-                    unsigned int* __restrict__ hist) {
-  __shared__ unsigned int h[4][HBINS];
-  for (int i = threadIdx.x; i < 4 * HBINS; i += SAMP_THREADS) (&h[0][0])[i] = 0;
-  __syncthreads();
-  const int sg = blockIdx.y, b = blockIdx.z;
-  const float* p = fs + (long long)b * cells;
-  const Philox rng(*seed_ptr);
+// ---- pass A: histogram of the cell probabilities of one pair (no random numbers; shared by all its streams) -------
+// A block covers SAMP_ELEMS_PER_BLOCK consecutive cells.  With VEC (N*N a multiple of 4, so every pair's row of cells
+// is 16-byte aligned) a thread issues its four float4 loads before touching any of them: with one scalar load in
+// flight per thread these passes were latency-bound at ~1.5 TB/s out of L2.
+template <bool VEC, typename F>
+__device__ __forceinline__ void for_each_cell(const float* __restrict__ p, long long cells, F&& f) {
   const long long e0 = (long long)blockIdx.x * SAMP_ELEMS_PER_BLOCK;
-  const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
-  for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) {
-    const float pv = p[e];
-    if (pv > 0.f) {
-      const uint4 r = rng((uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)sg, (uint32_t)b);
-      atomicAdd(&h[0][race_key(pv, r.x) >> 20], 1u);
-      atomicAdd(&h[1][race_key(pv, r.y) >> 20], 1u);
-      atomicAdd(&h[2][race_key(pv, r.z) >> 20], 1u);
-      atomicAdd(&h[3][race_key(pv, r.w) >> 20], 1u);
+  if (VEC) {
+    float4 v[4];
+    long long e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      e[i] = e0 + 4LL * (threadIdx.x + SAMP_THREADS * i);
+      v[i] = (e[i] < cells) ? __ldg(reinterpret_cast<const float4*>(p + e[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  }
-  __syncthreads();
-  for (int j = 0; j < 4; ++j) {
-    const int s = sg * 4 + j;
-    if (s >= IM) break;
-    unsigned int* dst = hist + ((long long)b * IM + s) * HBINS;
-    for (int i = threadIdx.x; i < HBINS; i += SAMP_THREADS)
-      if (h[j][i]) atomicAdd(dst + i, h[j][i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f(e[i], v[i].x); f(e[i] + 1, v[i].y); f(e[i] + 2, v[i].z); f(e[i] + 3, v[i].w);
+    }
+  } else {
+    const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
+    for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) f(e, p[e]);
   }
 }
 
-// threshold bin per stream: largest T with count(bin >= T) >= n_sample.  one 256-thread block per stream:
-// thread t owns the 8 bins [8t, 8t+8); a block-wide suffix sum locates the crossing.
+template <bool VEC>
+__global__ void __launch_bounds__(SAMP_THREADS)
+sampler_phist_kernel(const float* __restrict__ fs, long long cells, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int h[HBINS];
+  for (int i = threadIdx.x; i < HBINS; i += SAMP_THREADS) h[i] = 0;
+  __syncthreads();
+  const int b = blockIdx.y;
+  for_each_cell<VEC>(fs + (long long)b * cells, cells, [&](long long, float pv) {
+    if (pv > 0.f) atomicAdd(&h[__float_as_uint(pv) >> 20], 1u);
+  });
+  __syncthreads();
+  unsigned int* dst = hist + (long long)b * HBINS;
+  for (int i = threadIdx.x; i < HBINS; i += SAMP_THREADS)
+    if (h[i]) atomicAdd(dst + i, h[i]);
+}
+
+// ---- threshold ------------------------------------------------------------------------------------------------------
+// A cell survives the cut "key >= tau" with probability 1 - exp(-p / tau).  From the histogram, a LOWER bound of the
+// expected number of survivors f(tau) = sum_bins count * (1 - exp(-lower_edge / tau)) is evaluated on the grid of
+// bin edges and the largest tau with f(tau) >= n_sample + 8 sqrt(n_sample) + 16 is taken (bisection: f decreases in
+// tau).  The number of survivors of a stream is a sum of independent Bernoullis (variance <= mean), so fewer than
+// n_sample survive with probability < 1e-13; that event is reported through status bit 1 like "not enough nonzero
+// cells".  One 256-thread block per pair; thread t owns bins [8t, 8t+8).
 __global__ void __launch_bounds__(256)
-sampler_threshold_kernel(const unsigned int* __restrict__ hist, int n_streams, int n_sample, int* __restrict__ thr,
-                         int* __restrict__ status) {
-  __shared__ unsigned int wsum[8];
-  __shared__ int found;
-  const int s = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const unsigned int* h = hist + (long long)s * HBINS;
-  unsigned int c[8];
-  unsigned int mine = 0;
+sampler_tau_kernel(const unsigned int* __restrict__ hist, int n_sample, int* __restrict__ thr, float* __restrict__ inv_tau,
+                   int* __restrict__ status) {
+  __shared__ float wsum[8];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned int* h = hist + (long long)b * HBINS;
+  float c[8], edge[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { c[j] = h[t * 8 + j]; mine += c[j]; }
-  if (t == 0) found = -1;
-  // inclusive suffix sum over threads (thread 255 = highest bins)
-  unsigned int suf = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int v = __shfl_down_sync(0xffffffffu, suf, o);
-    if (lane + o < 32) suf += v;
+  for (int j = 0; j < 8; ++j) {
+    const int bin = t * 8 + j;
+    c[j] = (bin >= 1) ? (float)h[bin] : 0.f;
+    edge[j] = __uint_as_float((uint32_t)bin << 20);
   }
-  if (lane == 0) wsum[warp] = suf;
-  __syncthreads();
-  unsigned int above_warp = 0;
-  for (int w = warp + 1; w < 8; ++w) above_warp += wsum[w];
-  const unsigned int incl = suf + above_warp;          // count of bins >= 8t
-  const unsigned int excl = incl - mine;               // count of bins >= 8(t+1)
-  if (incl >= (unsigned)n_sample && excl < (unsigned)n_sample) {
-    unsigned int run = excl;
-    int T = t * 8;
-    for (int j = 7; j >= 0; --j) {
-      run += c[j];
-      if (run >= (unsigned)n_sample) { T = t * 8 + j; break; }
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) wsum[warp] = v;
+    __syncthreads();
+    return ((wsum[0] + wsum[1]) + (wsum[2] + wsum[3])) + ((wsum[4] + wsum[5]) + (wsum[6] + wsum[7]));
+  };
+  float mine = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine += c[j];
+  const float nonzero = block_sum(mine);
+  const float target = (float)n_sample + 8.0f * sqrtf((float)n_sample) + 16.0f;
+  // invariant: f(edge[lo]) >= target > f(edge[hi]).  lo == 7 stands for "tau below the normal floats": every nonzero
+  // cell is a candidate (f = nonzero).  Bins >= 2040 are inf / nan and never hold a probability.
+  int lo = 7, hi = HBINS - 9;
+  if (nonzero < target) hi = 8;                   // few nonzero cells: keep them all
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    const float it = 1.0f / __uint_as_float((uint32_t)mid << 20);
+    float f = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = edge[j] * it;
+      if (c[j] > 0.f) f += c[j] * ((y < 0.01f) ? y * (1.0f - 0.5f * y) : 1.0f - __expf(-y));   // empty bins may have inf / nan edges
     }
-    found = T;
+    f = block_sum(f);
+    if (f >= target) lo = mid; else hi = mid;
   }
-  __syncthreads();
   if (t == 0) {
-    int T = found;
-    // bin 0 holds the zero-probability cells (key 0): they may never be drawn (ATen raises in that case and
-    // the reference's try/except returns the zero pose, probabilisticProcrustes.py:331-342)
-    if (T <= 0) { T = 1; atomicOr(status, 1); }
-    thr[s] = T;
+    const float tau = __uint_as_float((uint32_t)lo << 20);
+    const bool all = (lo < 8);
+    thr[b] = all ? 1 : lo;
+    inv_tau[b] = all ? __int_as_float(0x7f800000) : 1.0f / tau;
+    // zero-probability cells may never be drawn (ATen raises in that case and the reference's try/except returns
+    // the zero pose, probabilisticProcrustes.py:331-342)
+    if (nonzero < (float)n_sample) atomicOr(status, 1);
   }
 }
 
-// ---- pass B: collect candidates (bin >= threshold) ---------------------------------------------------------
-// key >= tau  <=>  E <= p / tau  <=>  u <= 1 - exp(-p / tau), so almost every (cell, stream) is rejected with one
-// MUFU.EX2 and a compare (no log, no division); the exact key is recomputed only for the ~0.06 % that pass the
-// (slightly widened) cheap test, and the exact bin test of pass A decides.
+// ---- pass B: collect candidates (key bin >= threshold bin) -----------------------------------------------------------
+// key >= tau  <=>  E <= p / tau  <=>  u <= 1 - exp(-p / tau): one MUFU.EX2 per cell gives the (slightly widened) bound
+// that all IM streams of the pair share, one Philox call gives the 16-bit prefixes of 8 streams, and a stream's prefix
+// above the bound rejects it without a log or a division.  The exact key is computed only for the ~0.06 % that pass,
+// and its bin decides.
+template <bool VEC>
 __global__ void __launch_bounds__(SAMP_THREADS)
 sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
-                       const int* __restrict__ thr, unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt,
-                       int cap) {
-  const int sg = blockIdx.y, b = blockIdx.z;
-  const float* p = fs + (long long)b * cells;
+                       const int* __restrict__ thr, const float* __restrict__ inv_tau_p, unsigned long long* __restrict__ cand,
+                       unsigned int* __restrict__ cnt, int cap) {
+  const int b = blockIdx.y;
   const Philox rng(*seed_ptr);
-  int T[4];
-  float inv_tau[4];                    // 1 / tau, tau = lower edge of the threshold bin
+  const int T = thr[b];
+  const float inv_tau = inv_tau_p[b];
+  for_each_cell<VEC>(fs + (long long)b * cells, cells, [&](long long e, float pv) {
+    if (!(pv > 0.f)) return;
+    // u <= (1 - exp(-y)) * (1 + 2^-10) + 2^-30 with y = p / tau: a superset of the exact condition.  For small y
+    // 1 - exp(-y) <= y is used instead (1 - q would cancel catastrophically in fp32).
+    const float y = pv * inv_tau;
+    float q;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(-1.4426950408889634f * y));
+    const float prob = (y < 0.01f) ? y : 1.0f - q;
+    const float uth = fminf(fmaf(prob, 1.0009765625f, 9.3132257e-10f), 1.0f);
+    const uint32_t pth = (uint32_t)(uth * 65536.0f);                 // prefix > pth  =>  u > uth
+    for (int sg = 0; sg * 8 < IM; ++sg) {
+      const uint4 r = rng((uint32_t)e, (uint32_t)(e >> 32) ^ PHILOX_TAG_PREFIX, (uint32_t)sg, (uint32_t)b);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+      // any of the 8 prefixes at or below the bound?  (a cell passes with probability ~8 p / tau)
+      bool any = false;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    T[j] = (sg * 4 + j < IM) ? thr[(long long)b * IM + sg * 4 + j] : 0x7fffffff;
-    const float tau = __uint_as_float((uint32_t)(T[j] < 2047 ? T[j] : 2047) << 20);
-    inv_tau[j] = (sg * 4 + j < IM) ? 1.0f / tau : 0.0f;
-  }
-  const long long e0 = (long long)blockIdx.x * SAMP_ELEMS_PER_BLOCK;
-  const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
-  for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) {
-    const float pv = p[e];
-    if (pv > 0.f) {
-      const uint4 r = rng((uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)sg, (uint32_t)b);
-      const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // u <= (1 - exp(-y)) * (1 + 2^-10) + 2^-30 with y = p / tau: a superset of the exact condition.  For small y
-        // 1 - exp(-y) <= y is used instead (1 - q would cancel catastrophically in fp32).
-        const float y = pv * inv_tau[j];
-        float q;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(-1.4426950408889634f * y));
-        const float prob = (y < 0.01f) ? y : 1.0f - q;
-        const float uth = fmaf(prob, 1.0009765625f, 9.3132257e-10f);
-        const float u = ((float)bits[j] + 0.5f) * 2.3283064365386963e-10f;
-        if (u <= uth) {
-          const uint32_t k = race_key(pv, bits[j]);
-          if ((int)(k >> 20) >= T[j]) {
-            const long long s = (long long)b * IM + sg * 4 + j;
-            const unsigned int slot = atomicAdd(cnt + s, 1u);
-            if (slot < (unsigned)cap) cand[s * cap + slot] = ((unsigned long long)k << 32) | (uint32_t)e;
+      for (int j = 0; j < 4; ++j) any = any || ((w[j] & 0xffffu) <= pth) || ((w[j] >> 16) <= pth);
+      if (!any) continue;
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t prefix = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+        const int stream = sg * 8 + j;
+        if (prefix <= pth && stream < IM) {
+          const uint4 r2 = rng((uint32_t)e, (uint32_t)(e >> 32) ^ PHILOX_TAG_LOW, (uint32_t)stream, (uint32_t)b);
+          const float u = u_from_prefix(prefix, r2.x);
+          if (u <= uth) {
+            const uint32_t k = race_key(pv, u);
+            if ((int)(k >> 20) >= T) {
+              const long long s = (long long)b * IM + stream;
+              const unsigned int slot = atomicAdd(cnt + s, 1u);
+              if (slot < (unsigned)cap) cand[s * cap + slot] = ((unsigned long long)k << 32) | (uint32_t)e;
+            }
           }
         }
+      }
+    }
+  });
+}
+
+// ---- pass C: sort candidates, keep the n_sample largest -----------------------------------------------------
+// Bitonic sort (descending; key, then cell index: the result does not depend on the collection order) of one
+// stream's candidates by one 512-thread block.  Thread t keeps the E = SZ / 512 consecutive elements
+// [tE, tE + E) in registers: compare-exchange distances below E stay in the thread, distances up to 16 E are lane
+// shuffles, and only the remaining log2(SZ / (32 E)) distances per merge level go through shared memory (10 of the
+// 78 stages at SZ = 4096) -- a shared-memory-only network is bound by the SM's 128 B/clk of shared bandwidth.
+constexpr int SEL_THREADS = 512;
+
+template <int E, int J>
+__device__ __forceinline__ void select_local(unsigned long long (&v)[E], int base, int k) {
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    if ((r & J) == 0) {
+      const bool desc = (((base + r) & k) == 0);
+      const unsigned long long a = v[r], c = v[r | J];
+      const bool swap = desc ? (a < c) : (a > c);
+      v[r] = swap ? c : a; v[r | J] = swap ? a : c;
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void select_sort(unsigned long long (&v)[E], unsigned long long* sh, int t) {
+  constexpr int SZ = E * SEL_THREADS;
+  const int base = t * E;
+#pragma unroll 1
+  for (int k = 2; k <= SZ; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32 * E) {                       // partner element lives in another warp: through shared memory
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < E; ++r) sh[base + r] = v[r];
+        __syncthreads();
+        const int pbase = base ^ j;
+        const bool keep_max = (((base & j) == 0) == ((base & k) == 0));
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const unsigned long long o = sh[pbase + r];
+          v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
+        }
+      } else if (j >= E) {                     // partner element in the same warp, same register slot
+        const int lm = j / E;
+        const bool keep_max = (((base & j) == 0) == ((base & k) == 0));
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lm);
+          v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
+        }
+      } else {                                 // both elements in this thread (register indices must be static)
+        if (E > 8 && j == 8) select_local<E, 8>(v, base, k);
+        else if (E > 4 && j == 4) select_local<E, 4>(v, base, k);
+        else if (j == 2) select_local<E, 2>(v, base, k);
+        else select_local<E, 1>(v, base, k);
       }
     }
   }
 }
 
-// ---- pass C: sort candidates, keep the n_sample largest -----------------------------------------------------
+template <int E>
+__device__ __forceinline__ void select_run(const unsigned long long* __restrict__ src, int n, int n_sample,
+                                           int* __restrict__ dst, unsigned long long* sh) {
+  const int t = threadIdx.x;
+  unsigned long long v[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) v[r] = (t * E + r < n) ? src[t * E + r] : 0ull;
+  select_sort<E>(v, sh, t);
+#pragma unroll
+  for (int r = 0; r < E; ++r)
+    if (t * E + r < n_sample) dst[t * E + r] = (int)(uint32_t)v[r];
+}
+
 template <int CAP>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(SEL_THREADS)
 sampler_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, int n_sample,
                       int* __restrict__ idx_out, int* __restrict__ status) {
   extern __shared__ unsigned long long keys[];
@@ -188,33 +288,19 @@ sampler_select_kernel(const unsigned long long* __restrict__ cand, const unsigne
     if (n_raw > (unsigned)CAP) atomicOr(status, 2);     // candidate buffer overflow (selection truncated)
     if (n < n_sample) atomicOr(status, 1);
   }
-  // sort only the power of two that holds the candidates (typically ~2.3 k of them -> 4096)
-  int SZ = 2048;
-  while (SZ < n) SZ <<= 1;
-  for (int i = threadIdx.x; i < SZ; i += 1024) keys[i] = (i < n) ? cand[s * CAP + i] : 0ull;
-  __syncthreads();
-  // bitonic sort, descending
-  for (int k = 2; k <= SZ; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < SZ; i += 1024) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], c = keys[ixj];
-          const bool desc = ((i & k) == 0);
-          if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = threadIdx.x; i < n_sample; i += 1024) idx_out[s * n_sample + i] = (int)(uint32_t)keys[i];
+  // sort only the power of two that holds the candidates (typically ~2.6 k of them -> 4096)
+  const unsigned long long* src = cand + s * CAP;
+  int* dst = idx_out + s * n_sample;
+  if (n <= 2048) select_run<4>(src, n, n_sample, dst, keys);
+  else if (n <= 4096) select_run<8>(src, n, n_sample, dst, keys);
+  else select_run<16>(src, n, n_sample, dst, keys);
 }
 
 constexpr int CAND_CAP = 8192;
 
 size_t sampler_workspace_bytes(int B, int IM) {
   const size_t streams = (size_t)B * IM;
-  return streams * HBINS * 4 + streams * 4 /*thr*/ + streams * 4 /*cnt*/ + streams * CAND_CAP * 8 + 256;
+  return (size_t)B * HBINS * 4 + streams * 4 /*cnt*/ + (size_t)B * 8 /*thr, inv_tau*/ + streams * CAND_CAP * 8 + 512;
 }
 
 int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, const unsigned long long* seed, void* ws,
@@ -223,25 +309,29 @@ int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, 
   const long long cells = (long long)N * N;
   const size_t streams = (size_t)B * IM;
   uint8_t* w = reinterpret_cast<uint8_t*>(ws);
-  unsigned int* hist = reinterpret_cast<unsigned int*>(w); w += streams * HBINS * 4;
-  int* thr = reinterpret_cast<int*>(w); w += streams * 4;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(w); w += (size_t)B * HBINS * 4;
   unsigned int* cnt = reinterpret_cast<unsigned int*>(w); w += streams * 4;
+  int* thr = reinterpret_cast<int*>(w); w += (size_t)B * 4;
+  float* inv_tau = reinterpret_cast<float*>(w); w += (size_t)B * 4;
   w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w) + 255) & ~(uintptr_t)255);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(w);
-  MK_CUDA_CHECK(cudaMemsetAsync(hist, 0, streams * HBINS * 4 + streams * 8, st));
-  dim3 grid((unsigned)((cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK), ceil_div(IM, 4), B);
-  sampler_hist_kernel<<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, hist);
+  MK_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)B * HBINS * 4 + streams * 4, st));
+  dim3 grid((unsigned)((cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK), B);
+  const bool vec = (cells % 4 == 0) && (reinterpret_cast<uintptr_t>(final_scores) % 16 == 0);
+  if (vec) sampler_phist_kernel<true><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
+  else sampler_phist_kernel<false><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
   MK_CUDA_CHECK(cudaGetLastError());
-  sampler_threshold_kernel<<<(unsigned)streams, 256, 0, st>>>(hist, (int)streams, n_sample, thr, status);
+  sampler_tau_kernel<<<B, 256, 0, st>>>(hist, n_sample, thr, inv_tau, status);
   MK_CUDA_CHECK(cudaGetLastError());
-  sampler_collect_kernel<<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, cand, cnt, CAND_CAP);
+  if (vec) sampler_collect_kernel<true><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP);
+  else sampler_collect_kernel<false><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP);
   MK_CUDA_CHECK(cudaGetLastError());
   static bool attr = false;
   if (!attr) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(sampler_select_kernel<CAND_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
     attr = true;
   }
-  sampler_select_kernel<CAND_CAP><<<(unsigned)streams, 1024, CAND_CAP * 8, st>>>(cand, cnt, n_sample, idx_out, status);
+  sampler_select_kernel<CAND_CAP><<<(unsigned)streams, SEL_THREADS, CAND_CAP * 8, st>>>(cand, cnt, n_sample, idx_out, status);
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }

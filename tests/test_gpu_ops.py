@@ -278,6 +278,61 @@ def test_matcher_epilogues_vs_dual_softmax(impl, B, N):
     assert rel_err(fin, ref * s0[:, :, None].double() * s1[:, None, :].double()) < 1e-4
 
 
+def _philox4x32_7(c0, c1, c2, c3, seed):
+    """numpy restatement of the device generator (ransac.cu Philox): counters are uint32 arrays."""
+    import numpy as np
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    a, b = seed & 0xffffffff, seed >> 32
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint32).copy() for x in np.broadcast_arrays(c0, c1, c2, c3))
+    for _ in range(7):
+        p0, p1 = M0 * c0.astype(np.uint64), M1 * c2.astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & np.uint64(0xffffffff)).astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & np.uint64(0xffffffff)).astype(np.uint32)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint32(a), lo1, hi0 ^ c3 ^ np.uint32(b), lo0
+        a, b = (a + 0x9E3779B9) & 0xffffffff, (b + 0xBB67AE85) & 0xffffffff
+    return c0, c1, c2, c3
+
+
+@pytest.mark.parametrize("mode,N", [("spread", 120), ("few_nonzero", 120), ("spread", 121)])
+def test_outer_sampler_is_topk_of_the_race(mode, N):
+    """The kernel's draw must be exactly 'the n_s largest p / Exp(1) keys' of its own counter-based noise: the host
+    regenerates every cell's key for a stream (numpy Philox) and takes the top n_s by brute force.  Device log / divide
+    are approximate, so a handful of boundary keys may swap."""
+    import numpy as np
+    lib = _lib.load()
+    B, IM, n_s, seed = 2, 10, 2048, 0x1234567887654321      # N = 121: N*N is not a multiple of 4 (scalar load path)
+    cells = N * N
+    g = torch.Generator().manual_seed(3)
+    p = torch.rand(B, cells, generator=g) ** 6 * 1e-3
+    if mode == "few_nonzero":
+        p[:, torch.randperm(cells, generator=g)[: cells - 2100]] = 0      # 2100 nonzero cells: every one is a candidate
+    ws_bytes = lib.mk_op_sample_workspace_bytes(B, IM)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
+    idx = torch.full((B * IM, n_s), -1, dtype=torch.int32, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.check(lib.mk_op_sample(_lib.ptr(p.to(DEV)), B, N, IM, n_s, seed, _lib.ptr(ws), ws_bytes, _lib.ptr(idx), _lib.ptr(status), stream()))
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    idx = idx.cpu().numpy().reshape(B, IM, n_s)
+    e = np.arange(cells, dtype=np.uint32)
+    for b in range(B):
+        pb = p[b].numpy().astype(np.float64)
+        for s in (0, 7, 9):
+            sg, j = divmod(s, 8)
+            w = _philox4x32_7(e, np.uint32(0x5bd1e995), np.uint32(sg), np.uint32(b), seed)[j >> 1]
+            prefix = (w >> np.uint32((j & 1) * 16)) & np.uint32(0xffff)
+            low = _philox4x32_7(e, np.uint32(0x2545F491), np.uint32(s), np.uint32(b), seed)[0]
+            u = (prefix.astype(np.float64) + (low.astype(np.float64) + 0.5) * 2.0 ** -32) * 2.0 ** -16
+            key = np.where(pb > 0, pb / -np.log1p(-np.minimum(u, 0.99999994)), 0.0)
+            want = np.argsort(-key, kind="stable")[:n_s]
+            got = idx[b, s]
+            assert len(set(got.tolist())) == n_s
+            missing = set(want.tolist()) - set(got.tolist())
+            assert len(missing) <= 3, (mode, b, s, len(missing))
+            kg = key[got]                       # order: descending key, up to swaps of near-equal keys
+            assert np.all(kg[1:] <= kg[:-1] * (1 + 1e-3))
+
+
 def test_outer_sampler_properties():
     """Exponential-race sampler: distinct cells, never a zero-probability cell, heavy cells (almost) always
     drawn, light cells drawn in proportion to their mass."""

@@ -33,6 +33,11 @@ if "attention" in which:
     out = torch.empty(2 * T, D, dtype=torch.float16, device=dev)
     for _ in range(reps):
         _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), 2, T, D, 6, 0, stream()))
+if "attention_big" in which:   # ViT-B shape, full waves (8 images x 12 heads)
+    qkv = torch.randn(8 * T, 3 * 768, device=dev).half()
+    out = torch.empty(8 * T, 768, dtype=torch.float16, device=dev)
+    for _ in range(reps):
+        _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), 8, T, 768, 12, 0, stream()))
 if "conv" in which:         # heads resblock1 conv2: 4 groups x (512 -> 512, 3x3) over 2 padded 53x40 images
     h2, w2, G, Cc = 53, 40, 4, 512
     R = 2 * h2 * w2
