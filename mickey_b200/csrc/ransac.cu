@@ -56,8 +56,8 @@ constexpr uint32_t PHILOX_TAG_PREFIX = 0x5bd1e995u, PHILOX_TAG_LOW = 0x2545F491u
 // is 16-byte aligned) a thread issues its four float4 loads before touching any of them: with one scalar load in
 // flight per thread these passes were latency-bound at ~1.5 TB/s out of L2.
 template <bool VEC, typename F>
-__device__ __forceinline__ void for_each_cell(const float* __restrict__ p, long long cells, F&& f) {
-  const long long e0 = (long long)blockIdx.x * SAMP_ELEMS_PER_BLOCK;
+__device__ __forceinline__ void for_each_cell(const float* __restrict__ p, long long cells, long long chunk, F&& f) {
+  const long long e0 = chunk * SAMP_ELEMS_PER_BLOCK;
   if (VEC) {
     float4 v[4];
     long long e[4];
@@ -83,9 +83,11 @@ sampler_phist_kernel(const float* __restrict__ fs, long long cells, unsigned int
   for (int i = threadIdx.x; i < HBINS; i += SAMP_THREADS) h[i] = 0;
   __syncthreads();
   const int b = blockIdx.y;
-  for_each_cell<VEC>(fs + (long long)b * cells, cells, [&](long long, float pv) {
-    if (pv > 0.f) atomicAdd(&h[__float_as_uint(pv) >> 20], 1u);
-  });
+  const long long n_chunks = (cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)      // grid = whole waves of resident blocks
+    for_each_cell<VEC>(fs + (long long)b * cells, cells, chunk, [&](long long, float pv) {
+      if (pv > 0.f) atomicAdd(&h[__float_as_uint(pv) >> 20], 1u);
+    });
   __syncthreads();
   unsigned int* dst = hist + (long long)b * HBINS;
   for (int i = threadIdx.x; i < HBINS; i += SAMP_THREADS)
@@ -95,51 +97,71 @@ sampler_phist_kernel(const float* __restrict__ fs, long long cells, unsigned int
 // ---- threshold ------------------------------------------------------------------------------------------------------
 // A cell survives the cut "key >= tau" with probability 1 - exp(-p / tau).  From the histogram, a LOWER bound of the
 // expected number of survivors f(tau) = sum_bins count * (1 - exp(-lower_edge / tau)) is evaluated on the grid of
-// bin edges and the largest tau with f(tau) >= n_sample + 8 sqrt(n_sample) + 16 is taken (bisection: f decreases in
-// tau).  The number of survivors of a stream is a sum of independent Bernoullis (variance <= mean), so fewer than
-// n_sample survive with probability < 1e-13; that event is reported through status bit 1 like "not enough nonzero
-// cells".  One 256-thread block per pair; thread t owns bins [8t, 8t+8).
-__global__ void __launch_bounds__(256)
+// bin edges and the largest tau with f(tau) >= n_sample + 8 sqrt(n_sample) + 16 is taken (f decreases in tau).  The
+// number of survivors of a stream is a sum of independent Bernoullis (variance <= mean), so fewer than n_sample
+// survive with probability < 1e-13; that event is reported through status bit 1 like "not enough nonzero cells".
+// One 1024-thread block per pair runs a 33-ary search: each round, warp w evaluates f at its own grid point (64 bins
+// per lane, fixed-order shuffle reduction), so three rounds replace eleven bisection steps of block-wide reductions.
+constexpr int TAU_THREADS = 1024;
+
+__global__ void __launch_bounds__(TAU_THREADS)
 sampler_tau_kernel(const unsigned int* __restrict__ hist, int n_sample, int* __restrict__ thr, float* __restrict__ inv_tau,
                    int* __restrict__ status) {
-  __shared__ float wsum[8];
+  __shared__ float cc[HBINS], ee[HBINS];          // counts and lower edges of the occupied bins, in bin order
+  __shared__ int wtot[32];
+  __shared__ float fw[32];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const unsigned int* h = hist + (long long)b * HBINS;
-  float c[8], edge[8];
+  // compact the occupied bins (a few hundred of the 2048): thread t owns bins 2t, 2t+1; bin 0 (p == 0) and the
+  // inf / nan bins >= 2040 never take part
+  const int b0 = 2 * t, b1 = 2 * t + 1;
+  const unsigned int c0 = (b0 >= 1 && b0 < HBINS - 8) ? h[b0] : 0u, c1 = (b1 < HBINS - 8) ? h[b1] : 0u;
+  const int k = (c0 > 0) + (c1 > 0);
+  int incl = k;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int bin = t * 8 + j;
-    c[j] = (bin >= 1) ? (float)h[bin] : 0.f;
-    edge[j] = __uint_as_float((uint32_t)bin << 20);
-  }
-  auto block_sum = [&](float v) {
+  for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  int off = incl - k, nnz = 0;
+  for (int w = 0; w < 32; ++w) { const int x = wtot[w]; if (w < warp) off += x; nnz += x; }
+  if (c0 > 0) { cc[off] = (float)c0; ee[off] = __uint_as_float((uint32_t)b0 << 20); ++off; }
+  if (c1 > 0) { cc[off] = (float)c1; ee[off] = __uint_as_float((uint32_t)b1 << 20); }
+  __syncthreads();
+  auto warp_sum = [&](float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if (lane == 0) wsum[warp] = v;
-    __syncthreads();
-    return ((wsum[0] + wsum[1]) + (wsum[2] + wsum[3])) + ((wsum[4] + wsum[5]) + (wsum[6] + wsum[7]));
+    return v;
   };
-  float mine = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) mine += c[j];
-  const float nonzero = block_sum(mine);
+  float nz = 0.f;
+  for (int i = lane; i < nnz; i += 32) nz += cc[i];
+  const float nonzero = warp_sum(nz);             // every warp computes the same value in the same order
   const float target = (float)n_sample + 8.0f * sqrtf((float)n_sample) + 16.0f;
   // invariant: f(edge[lo]) >= target > f(edge[hi]).  lo == 7 stands for "tau below the normal floats": every nonzero
-  // cell is a candidate (f = nonzero).  Bins >= 2040 are inf / nan and never hold a probability.
+  // cell is a candidate (f = nonzero).
   int lo = 7, hi = HBINS - 9;
   if (nonzero < target) hi = 8;                   // few nonzero cells: keep them all
   while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    const float it = 1.0f / __uint_as_float((uint32_t)mid << 20);
-    float f = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float y = edge[j] * it;
-      if (c[j] > 0.f) f += c[j] * ((y < 0.01f) ? y * (1.0f - 0.5f * y) : 1.0f - __expf(-y));   // empty bins may have inf / nan edges
+    const int mid = lo + (int)(((long long)(hi - lo) * (warp + 1)) / 33);   // lo <= mid < hi, non-decreasing in warp
+    float f = target;                             // mid == lo: known to satisfy the invariant
+    if (mid > lo) {
+      const float it = 1.0f / __uint_as_float((uint32_t)mid << 20);
+      f = 0.f;
+      for (int i = lane; i < nnz; i += 32) {
+        const float y = ee[i] * it;
+        f += cc[i] * ((y < 0.01f) ? y * (1.0f - 0.5f * y) : 1.0f - __expf(-y));
+      }
+      f = warp_sum(f);
     }
-    f = block_sum(f);
-    if (f >= target) lo = mid; else hi = mid;
+    __syncthreads();
+    if (lane == 0) fw[warp] = f;
+    __syncthreads();
+    // largest warp whose point still reaches the target -> new lo; the next warp's point (or hi) -> new hi
+    int best = -1;
+    for (int w = 0; w < 32; ++w) if (fw[w] >= target) best = w;
+    const int span = hi - lo;
+    const int new_lo = (best >= 0) ? lo + (int)(((long long)span * (best + 1)) / 33) : lo;
+    const int new_hi = (best < 31) ? lo + (int)(((long long)span * (best + 2)) / 33) : hi;
+    lo = new_lo; hi = (new_hi > new_lo) ? new_hi : new_lo + 1;
   }
   if (t == 0) {
     const float tau = __uint_as_float((uint32_t)lo << 20);
@@ -157,6 +179,29 @@ sampler_tau_kernel(const unsigned int* __restrict__ hist, int n_sample, int* __r
 // that all IM streams of the pair share, one Philox call gives the 16-bit prefixes of 8 streams, and a stream's prefix
 // above the bound rejects it without a log or a division.  The exact key is computed only for the ~0.06 % that pass,
 // and its bin decides.
+// rare path (a cell passes with probability ~8 p / tau): kept out of line so that the per-cell loop stays a few dozen
+// instructions (inlined 16 times per thread it overflowed the instruction cache: 12 'no_instruction' stall cycles per issue)
+__device__ __noinline__ void collect_refine(const Philox& rng, long long e, float pv, float uth, uint32_t pth, uint4 r, int sg, int b,
+                                            int IM, int T, unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, int cap) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t prefix = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+    const int stream = sg * 8 + j;
+    if (prefix <= pth && stream < IM) {
+      const uint4 r2 = rng((uint32_t)e, (uint32_t)(e >> 32) ^ PHILOX_TAG_LOW, (uint32_t)stream, (uint32_t)b);
+      const float u = u_from_prefix(prefix, r2.x);
+      if (u <= uth) {
+        const uint32_t k = race_key(pv, u);
+        if ((int)(k >> 20) >= T) {
+          const long long s = (long long)b * IM + stream;
+          const unsigned int slot = atomicAdd(cnt + s, 1u);
+          if (slot < (unsigned)cap) cand[s * cap + slot] = ((unsigned long long)k << 32) | (uint32_t)e;
+        }
+      }
+    }
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(SAMP_THREADS)
 sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
@@ -166,7 +211,8 @@ sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, co
   const Philox rng(*seed_ptr);
   const int T = thr[b];
   const float inv_tau = inv_tau_p[b];
-  for_each_cell<VEC>(fs + (long long)b * cells, cells, [&](long long e, float pv) {
+  const float* p = fs + (long long)b * cells;
+  auto cell = [&](long long e, float pv) {
     if (!(pv > 0.f)) return;
     // u <= (1 - exp(-y)) * (1 + 2^-10) + 2^-30 with y = p / tau: a superset of the exact condition.  For small y
     // 1 - exp(-y) <= y is used instead (1 - q would cancel catastrophically in fp32).
@@ -178,109 +224,160 @@ sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, co
     const uint32_t pth = (uint32_t)(uth * 65536.0f);                 // prefix > pth  =>  u > uth
     for (int sg = 0; sg * 8 < IM; ++sg) {
       const uint4 r = rng((uint32_t)e, (uint32_t)(e >> 32) ^ PHILOX_TAG_PREFIX, (uint32_t)sg, (uint32_t)b);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-      // any of the 8 prefixes at or below the bound?  (a cell passes with probability ~8 p / tau)
-      bool any = false;
+      // any of the 8 16-bit prefixes at or below the bound?
+      const bool any = ((r.x & 0xffffu) <= pth) | ((r.x >> 16) <= pth) | ((r.y & 0xffffu) <= pth) | ((r.y >> 16) <= pth) |
+                       ((r.z & 0xffffu) <= pth) | ((r.z >> 16) <= pth) | ((r.w & 0xffffu) <= pth) | ((r.w >> 16) <= pth);
+      if (any) collect_refine(rng, e, pv, uth, pth, r, sg, b, IM, T, cand, cnt, cap);
+    }
+  };
+  const long long n_chunks = (cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {    // grid = whole waves of resident blocks
+    const long long e0 = chunk * SAMP_ELEMS_PER_BLOCK;
+    if (VEC) {
+      float4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) any = any || ((w[j] & 0xffffu) <= pth) || ((w[j] >> 16) <= pth);
-      if (!any) continue;
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t prefix = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-        const int stream = sg * 8 + j;
-        if (prefix <= pth && stream < IM) {
-          const uint4 r2 = rng((uint32_t)e, (uint32_t)(e >> 32) ^ PHILOX_TAG_LOW, (uint32_t)stream, (uint32_t)b);
-          const float u = u_from_prefix(prefix, r2.x);
-          if (u <= uth) {
-            const uint32_t k = race_key(pv, u);
-            if ((int)(k >> 20) >= T) {
-              const long long s = (long long)b * IM + stream;
-              const unsigned int slot = atomicAdd(cnt + s, 1u);
-              if (slot < (unsigned)cap) cand[s * cap + slot] = ((unsigned long long)k << 32) | (uint32_t)e;
-            }
-          }
+      for (int i = 0; i < 4; ++i) {
+        const long long e = e0 + 4LL * (threadIdx.x + SAMP_THREADS * i);
+        v[i] = (e < cells) ? __ldg(reinterpret_cast<const float4*>(p + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {        // component-major: the loop body holds four (not sixteen) copies of cell()
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pv = (c == 0) ? v[i].x : (c == 1) ? v[i].y : (c == 2) ? v[i].z : v[i].w;
+          cell(e0 + 4LL * (threadIdx.x + SAMP_THREADS * i) + c, pv);
         }
       }
-    }
-  });
-}
-
-// ---- pass C: sort candidates, keep the n_sample largest -----------------------------------------------------
-// Bitonic sort (descending; key, then cell index: the result does not depend on the collection order) of one
-// stream's candidates by one 512-thread block.  Thread t keeps the E = SZ / 512 consecutive elements
-// [tE, tE + E) in registers: compare-exchange distances below E stay in the thread, distances up to 16 E are lane
-// shuffles, and only the remaining log2(SZ / (32 E)) distances per merge level go through shared memory (10 of the
-// 78 stages at SZ = 4096) -- a shared-memory-only network is bound by the SM's 128 B/clk of shared bandwidth.
-constexpr int SEL_THREADS = 512;
-
-template <int E, int J>
-__device__ __forceinline__ void select_local(unsigned long long (&v)[E], int base, int k) {
-#pragma unroll
-  for (int r = 0; r < E; ++r) {
-    if ((r & J) == 0) {
-      const bool desc = (((base + r) & k) == 0);
-      const unsigned long long a = v[r], c = v[r | J];
-      const bool swap = desc ? (a < c) : (a > c);
-      v[r] = swap ? c : a; v[r | J] = swap ? a : c;
+    } else {
+      const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
+      for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) cell(e, p[e]);
     }
   }
 }
 
-template <int E>
-__device__ __forceinline__ void select_sort(unsigned long long (&v)[E], unsigned long long* sh, int t) {
-  constexpr int SZ = E * SEL_THREADS;
-  const int base = t * E;
+// ---- pass C: keep the n_sample largest keys -------------------------------------------------------------------------
+// One 512-thread block per stream; the candidates (key << 32 | cell, all distinct) sit in registers.
+//   1. radix select, most significant byte first: a 256-bin histogram of the current byte among the elements that
+//      still match the boundary prefix, a suffix scan, the bin where the running count crosses what is still needed.
+//      It stops as soon as the boundary bin is taken whole (normally after the four key bytes).
+//   2. the selected cells are compacted into shared memory and sorted ascending by cell index (32-bit bitonic network,
+//      4 elements per thread: in-thread, shuffle and shared-memory stages), so the result does not depend on the order
+//      in which pass B happened to append the candidates.  The order of a draw carries no information for the solver
+//      (ATen's multinomial returns key order; the reference uses the draw as a set).
+// Sorting the 64-bit candidates themselves was ALU-bound on the 8 active SMs (40 us for 8 streams).
+constexpr int SEL_THREADS = 512;
+
+template <int J>
+__device__ __forceinline__ void sort4_local(uint32_t (&v)[4], int base, int k) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if ((r & J) == 0) {
+      const bool asc = (((base + r) & k) == 0);
+      const uint32_t a = v[r], c = v[r | J];
+      const uint32_t lo = min(a, c), hi = max(a, c);
+      v[r] = asc ? lo : hi; v[r | J] = asc ? hi : lo;
+    }
+  }
+}
+
+// ascending bitonic sort of SZ = 2048 values, element i = 4 t + r
+__device__ __forceinline__ void sort2048_u32(uint32_t (&v)[4], uint32_t* sh, int t) {
+  constexpr int SZ = 4 * SEL_THREADS;
+  const int base = t * 4;
 #pragma unroll 1
   for (int k = 2; k <= SZ; k <<= 1) {
 #pragma unroll 1
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 32 * E) {                       // partner element lives in another warp: through shared memory
+      const bool keep_min = (((base & j) == 0) == ((base & k) == 0));   // used when the partner is in another thread
+      if (j >= 128) {
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < E; ++r) sh[base + r] = v[r];
+        for (int r = 0; r < 4; ++r) sh[base + r] = v[r];
         __syncthreads();
         const int pbase = base ^ j;
-        const bool keep_max = (((base & j) == 0) == ((base & k) == 0));
 #pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const unsigned long long o = sh[pbase + r];
-          v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
-        }
-      } else if (j >= E) {                     // partner element in the same warp, same register slot
-        const int lm = j / E;
-        const bool keep_max = (((base & j) == 0) == ((base & k) == 0));
+        for (int r = 0; r < 4; ++r) { const uint32_t o = sh[pbase + r]; v[r] = keep_min ? min(v[r], o) : max(v[r], o); }
+      } else if (j >= 4) {
 #pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lm);
-          v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] < o ? v[r] : o);
-        }
-      } else {                                 // both elements in this thread (register indices must be static)
-        if (E > 8 && j == 8) select_local<E, 8>(v, base, k);
-        else if (E > 4 && j == 4) select_local<E, 4>(v, base, k);
-        else if (j == 2) select_local<E, 2>(v, base, k);
-        else select_local<E, 1>(v, base, k);
+        for (int r = 0; r < 4; ++r) { const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j >> 2); v[r] = keep_min ? min(v[r], o) : max(v[r], o); }
+      } else if (j == 2) {
+        sort4_local<2>(v, base, k);
+      } else {
+        sort4_local<1>(v, base, k);
       }
     }
   }
 }
 
 template <int E>
-__device__ __forceinline__ void select_run(const unsigned long long* __restrict__ src, int n, int n_sample,
-                                           int* __restrict__ dst, unsigned long long* sh) {
-  const int t = threadIdx.x;
+__device__ __forceinline__ void select_run(const unsigned long long* __restrict__ src, int n, int n_sample, int* __restrict__ dst,
+                                           unsigned int* hist, uint32_t* sel, int* ctrl) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   unsigned long long v[E];
 #pragma unroll
-  for (int r = 0; r < E; ++r) v[r] = (t * E + r < n) ? src[t * E + r] : 0ull;
-  select_sort<E>(v, sh, t);
+  for (int r = 0; r < E; ++r) v[r] = (t + SEL_THREADS * r < n) ? src[t + SEL_THREADS * r] : 0ull;   // 0 < every real candidate
+  // ---- 1. radix select of the n_sample-th largest
+  unsigned long long prefix = 0;         // bytes already fixed (value of v >> (shift + 8) of the boundary element)
+  int need = n_sample;                   // how many must still come out of the elements matching the prefix
+  int shift = 56;
+  bool whole = false;                    // boundary bin taken whole: selection = (v >> shift) >= boundary value
+  unsigned long long bound = 0;
+  while (true) {
+    if (t < 256) hist[t] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+      if (shift == 56 || (v[r] >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(v[r] >> shift) & 0xffu], 1u);
+    __syncthreads();
+    if (warp == 0) {                     // suffix counts over the 256 bins: lane owns bins [8 lane, 8 lane + 8)
+      unsigned int c[8], mine = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; mine += c[i]; }
+      unsigned int suf = mine;           // inclusive suffix sum over lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += x; }
+      const unsigned int above = suf - mine;          // elements in bins of higher lanes
+      if (above < (unsigned)need && suf >= (unsigned)need) {
+        unsigned int run = above;
+        for (int i = 7; i >= 0; --i) {
+          if (run + c[i] >= (unsigned)need) { ctrl[0] = lane * 8 + i; ctrl[1] = need - (int)run; ctrl[2] = (int)c[i]; break; }
+          run += c[i];
+        }
+      }
+    }
+    __syncthreads();
+    const int digit = ctrl[0], need_in = ctrl[1], have_in = ctrl[2];
+    __syncthreads();
+    bound = (prefix << 8) | (unsigned)digit;
+    if (have_in == need_in || shift == 0) { whole = true; break; }
+    prefix = bound; need = need_in; shift -= 8;
+  }
+  (void)whole;
+  // ---- 2. compact the selected cells, sort them by cell index
+  if (t == 0) ctrl[3] = 0;
+  __syncthreads();
 #pragma unroll
   for (int r = 0; r < E; ++r)
-    if (t * E + r < n_sample) dst[t * E + r] = (int)(uint32_t)v[r];
+    if (v[r] != 0ull && (v[r] >> shift) >= bound) { const int slot = atomicAdd(&ctrl[3], 1); if (slot < 4 * SEL_THREADS) sel[slot] = (uint32_t)v[r]; }
+  __syncthreads();
+  const int got = min(ctrl[3], 4 * SEL_THREADS);
+  uint32_t c4[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) c4[r] = (4 * t + r < got) ? sel[4 * t + r] : 0xffffffffu;
+  __syncthreads();
+  sort2048_u32(c4, sel, t);
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (4 * t + r < n_sample) dst[4 * t + r] = (4 * t + r < got) ? (int)c4[r] : 0;
 }
 
 template <int CAP>
 __global__ void __launch_bounds__(SEL_THREADS)
 sampler_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, int n_sample,
                       int* __restrict__ idx_out, int* __restrict__ status) {
-  extern __shared__ unsigned long long keys[];
+  __shared__ unsigned int hist[256];
+  __shared__ uint32_t sel[4 * SEL_THREADS];
+  __shared__ int ctrl[4];
   const long long s = blockIdx.x;
   const unsigned int n_raw = cnt[s];
   const int n = (int)min(n_raw, (unsigned)CAP);
@@ -288,12 +385,15 @@ sampler_select_kernel(const unsigned long long* __restrict__ cand, const unsigne
     if (n_raw > (unsigned)CAP) atomicOr(status, 2);     // candidate buffer overflow (selection truncated)
     if (n < n_sample) atomicOr(status, 1);
   }
-  // sort only the power of two that holds the candidates (typically ~2.6 k of them -> 4096)
   const unsigned long long* src = cand + s * CAP;
   int* dst = idx_out + s * n_sample;
-  if (n <= 2048) select_run<4>(src, n, n_sample, dst, keys);
-  else if (n <= 4096) select_run<8>(src, n, n_sample, dst, keys);
-  else select_run<16>(src, n, n_sample, dst, keys);
+  if (n < n_sample) {                                   // not enough candidates: status bit 1 is set, the pose is zeroed
+    for (int i = threadIdx.x; i < n_sample; i += SEL_THREADS) dst[i] = (i < n) ? (int)(uint32_t)src[i] : 0;
+    return;
+  }
+  if (n <= 4 * SEL_THREADS) select_run<4>(src, n, n_sample, dst, hist, sel, ctrl);
+  else if (n <= 8 * SEL_THREADS) select_run<8>(src, n, n_sample, dst, hist, sel, ctrl);
+  else select_run<16>(src, n, n_sample, dst, hist, sel, ctrl);
 }
 
 constexpr int CAND_CAP = 8192;
@@ -316,22 +416,20 @@ int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, 
   w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w) + 255) & ~(uintptr_t)255);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(w);
   MK_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)B * HBINS * 4 + streams * 4, st));
-  dim3 grid((unsigned)((cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK), B);
+  // one block per 4096-cell chunk (the hardware block scheduler balances the 1.5 waves at chunk granularity); the
+  // kernels loop over chunks so that a smaller grid stays correct
+  dim3 grid((unsigned)min((cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK, 65535LL * 16), B);
   const bool vec = (cells % 4 == 0) && (reinterpret_cast<uintptr_t>(final_scores) % 16 == 0);
   if (vec) sampler_phist_kernel<true><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
   else sampler_phist_kernel<false><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
   MK_CUDA_CHECK(cudaGetLastError());
-  sampler_tau_kernel<<<B, 256, 0, st>>>(hist, n_sample, thr, inv_tau, status);
+  sampler_tau_kernel<<<B, TAU_THREADS, 0, st>>>(hist, n_sample, thr, inv_tau, status);
   MK_CUDA_CHECK(cudaGetLastError());
   if (vec) sampler_collect_kernel<true><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP);
   else sampler_collect_kernel<false><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP);
   MK_CUDA_CHECK(cudaGetLastError());
-  static bool attr = false;
-  if (!attr) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(sampler_select_kernel<CAND_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
-    attr = true;
-  }
-  sampler_select_kernel<CAND_CAP><<<(unsigned)streams, SEL_THREADS, CAND_CAP * 8, st>>>(cand, cnt, n_sample, idx_out, status);
+  if (n_sample > 4 * SEL_THREADS) { set_last_error("NUM_SAMPLED_MATCHES %d too large", n_sample); return MK_ERR_UNSUPPORTED; }
+  sampler_select_kernel<CAND_CAP><<<(unsigned)streams, SEL_THREADS, 0, st>>>(cand, cnt, n_sample, idx_out, status);
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }

@@ -297,7 +297,7 @@ def _philox4x32_7(c0, c1, c2, c3, seed):
 def test_outer_sampler_is_topk_of_the_race(mode, N):
     """The kernel's draw must be exactly 'the n_s largest p / Exp(1) keys' of its own counter-based noise: the host
     regenerates every cell's key for a stream (numpy Philox) and takes the top n_s by brute force.  Device log / divide
-    are approximate, so a handful of boundary keys may swap."""
+    are approximate, so a handful of keys at the boundary may differ."""
     import numpy as np
     lib = _lib.load()
     B, IM, n_s, seed = 2, 10, 2048, 0x1234567887654321      # N = 121: N*N is not a multiple of 4 (scalar load path)
@@ -329,8 +329,7 @@ def test_outer_sampler_is_topk_of_the_race(mode, N):
             assert len(set(got.tolist())) == n_s
             missing = set(want.tolist()) - set(got.tolist())
             assert len(missing) <= 3, (mode, b, s, len(missing))
-            kg = key[got]                       # order: descending key, up to swaps of near-equal keys
-            assert np.all(kg[1:] <= kg[:-1] * (1 + 1e-3))
+            assert np.all(got[1:] > got[:-1])   # canonical order of a draw: ascending cell index
 
 
 def test_outer_sampler_properties():
