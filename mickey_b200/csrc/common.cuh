@@ -76,7 +76,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 
-bool pdl_enabled();
+bool pdl_enabled();   // default on; MICKEY_PDL=0 disables
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -166,10 +166,10 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
 
 bool pdl_enabled() {
   static int v = -1;
-  // opt-in: measured on B200 (profiles/r01_notes.md) PDL was 2-3 % slower for this pipeline inside a CUDA graph —
-  // early-launched CTAs hold shared memory / TMEM while they wait, which costs the primary kernel's later waves more
-  // than the overlapped prologues save.
-  if (v < 0) { const char* e = getenv("MICKEY_PDL"); v = (e && strcmp(e, "1") == 0) ? 1 : 0; }
+  // on by default (MICKEY_PDL=0 disables): with three steps in flight it measured +5.7 % pairs/s on the C2 workload
+  // (775 vs 734, profiles/r01_notes.md).  An earlier build, with thread-per-row epilogues and no pipelining, was 2-3 %
+  // slower with it -- re-measure when the kernels change.
+  if (v < 0) { const char* e = getenv("MICKEY_PDL"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
   return v == 1;
 }
 

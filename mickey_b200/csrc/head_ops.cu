@@ -26,6 +26,8 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v + 1.0f : exp
 constexpr int KV_ROWS = 32;
 __global__ void __launch_bounds__(256)
 linattn_kv_kernel(const float* __restrict__ qkv, float* __restrict__ kvout, int G, int h2, int w2) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   __shared__ float Ks[KV_ROWS][128 + 4];
   __shared__ float Vs[KV_ROWS][128 + 4];
   const int g = blockIdx.y, im = blockIdx.z;
@@ -70,6 +72,8 @@ linattn_kv_kernel(const float* __restrict__ qkv, float* __restrict__ kvout, int 
 // grid (ceil(2176/128), G, n_img), 128 threads; 8 independent loads in flight per thread.
 __global__ void __launch_bounds__(128)
 linattn_kv_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int G, int chunks) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   const int g = blockIdx.y, im = blockIdx.z;
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= 8 * 272) return;
@@ -89,6 +93,8 @@ linattn_kv_reduce_kernel(const float* __restrict__ part, float* __restrict__ out
 __global__ void __launch_bounds__(256)
 linattn_msg_kernel(const float* __restrict__ qkv, const float* __restrict__ kv, __half* __restrict__ msg, int G, int h2,
                    int w2, float eps) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   __shared__ float KVs[8][272];
   const int g = blockIdx.y, im = blockIdx.z, t = threadIdx.x;
   const int per_img = h2 * w2;
@@ -133,14 +139,14 @@ int linattn_kv_chunks(int h2, int w2) { return ceil_div(h2 * w2, KV_ROWS); }
 
 int linattn_kv(const float* qkv, float* kv_part, float* kv, int n_img, int G, int h2, int w2, cudaStream_t s) {
   const int chunks = linattn_kv_chunks(h2, w2);
-  linattn_kv_kernel<<<dim3(chunks, G, n_img), 256, 0, s>>>(qkv, kv_part, G, h2, w2);
+  MK_CUDA_CHECK(launch_k(linattn_kv_kernel, dim3(chunks, G, n_img), dim3(256), 0, s, qkv, kv_part, G, h2, w2));
   MK_CUDA_CHECK(cudaGetLastError());
-  linattn_kv_reduce_kernel<<<dim3(ceil_div(8 * 272, 128), G, n_img), 128, 0, s>>>(kv_part, kv, G, chunks);
+  MK_CUDA_CHECK(launch_k(linattn_kv_reduce_kernel, dim3(ceil_div(8 * 272, 128), G, n_img), dim3(128), 0, s, kv_part, kv, G, chunks));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
 int linattn_msg(const float* qkv, const float* kv, void* msg, int n_img, int G, int h2, int w2, float eps, cudaStream_t s) {
-  linattn_msg_kernel<<<dim3(ceil_div(h2 * w2, 32), G, n_img), 256, 0, s>>>(qkv, kv, (__half*)msg, G, h2, w2, eps);
+  MK_CUDA_CHECK(launch_k(linattn_msg_kernel, dim3(ceil_div(h2 * w2, 32), G, n_img), dim3(256), 0, s, qkv, kv, (__half*)msg, G, h2, w2, eps));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
@@ -158,6 +164,8 @@ kp_head_out_kernel(const float* __restrict__ y, const float* __restrict__ w_dept
                    const float* __restrict__ w_score, float* __restrict__ depth, float* __restrict__ kps,
                    float* __restrict__ score_raw, int n_img, int gh, int gw, int depth_sigmoid, float max_depth,
                    float down_factor) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   const int tok = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int N = gh * gw;
   if (tok >= n_img * N) return;
@@ -189,6 +197,8 @@ kp_head_out_kernel(const float* __restrict__ y, const float* __restrict__ w_dept
 __global__ void __launch_bounds__(256)
 score_activation_kernel(const float* __restrict__ raw, float* __restrict__ scr, int gh, int gw, int use_softmax,
                         int border, float temp, float eps) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   __shared__ float red[256];
   const int im = blockIdx.x, N = gh * gw, t = threadIdx.x;
   const float* r = raw + (long long)im * N;
@@ -224,10 +234,10 @@ score_activation_kernel(const float* __restrict__ raw, float* __restrict__ scr, 
 int kp_head_out(const float* y, const float* w_depth, const float* w_xy, const float* w_score, float* depth, float* kps,
                 float* score_raw, float* scr, int n_img, int gh, int gw, int depth_sigmoid, float max_depth,
                 float down_factor, int use_softmax, cudaStream_t s) {
-  kp_head_out_kernel<<<ceil_div(n_img * gh * gw, 8), 256, 0, s>>>(y, w_depth, w_xy, w_score, depth, kps, score_raw, n_img,
-                                                                    gh, gw, depth_sigmoid, max_depth, down_factor);
+  MK_CUDA_CHECK(launch_k(kp_head_out_kernel, dim3(ceil_div(n_img * gh * gw, 8)), dim3(256), 0, s, y, w_depth, w_xy, w_score, depth, kps, score_raw, n_img,
+                                                                    gh, gw, depth_sigmoid, max_depth, down_factor));
   MK_CUDA_CHECK(cudaGetLastError());
-  score_activation_kernel<<<n_img, 256, 0, s>>>(score_raw, scr, gh, gw, use_softmax, 3, 100.0f, 1e-16f);
+  MK_CUDA_CHECK(launch_k(score_activation_kernel, dim3(n_img), dim3(256), 0, s, score_raw, scr, gh, gw, use_softmax, 3, 100.0f, 1e-16f));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
@@ -244,6 +254,8 @@ int kp_head_out(const float* y, const float* w_depth, const float* w_xy, const f
 __global__ void __launch_bounds__(256)
 desc_out_kernel(const float* __restrict__ y, float* __restrict__ dsc_cm, __half* __restrict__ dsc_x,
                 float* __restrict__ nrm2, int n_img, int gh, int gw, int normalize) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   const int tok = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int N = gh * gw;
   if (tok >= n_img * N) return;
@@ -282,7 +294,7 @@ desc_out_kernel(const float* __restrict__ y, float* __restrict__ dsc_cm, __half*
 
 int desc_out(const float* y, float* dsc_cm, void* dsc_x, float* nrm2, int n_img, int gh, int gw, int normalize,
              cudaStream_t s) {
-  desc_out_kernel<<<ceil_div(n_img * gh * gw, 8), 256, 0, s>>>(y, dsc_cm, (__half*)dsc_x, nrm2, n_img, gh, gw, normalize);
+  MK_CUDA_CHECK(launch_k(desc_out_kernel, dim3(ceil_div(n_img * gh * gw, 8)), dim3(256), 0, s, y, dsc_cm, (__half*)dsc_x, nrm2, n_img, gh, gw, normalize));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
@@ -293,6 +305,8 @@ int desc_out(const float* y, float* dsc_cm, void* dsc_x, float* nrm2, int n_img,
 __global__ void __launch_bounds__(256)
 matcher_prep_kernel(const float* __restrict__ nrm2, const float* __restrict__ dustbin, float inv_temp,
                     float* __restrict__ shift, int B, int N) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   __shared__ float r0[256], r1[256];
   const int b = blockIdx.x, t = threadIdx.x;
   float m0 = 0.f, m1 = 0.f;
@@ -314,7 +328,7 @@ matcher_prep_kernel(const float* __restrict__ nrm2, const float* __restrict__ du
 }
 
 int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float* shift, int B, int N, cudaStream_t s) {
-  matcher_prep_kernel<<<B, 256, 0, s>>>(nrm2, dustbin, inv_temp, shift, B, N);
+  MK_CUDA_CHECK(launch_k(matcher_prep_kernel, dim3(B), dim3(256), 0, s, nrm2, dustbin, inv_temp, shift, B, N));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }

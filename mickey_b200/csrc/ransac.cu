@@ -107,6 +107,8 @@ constexpr int TAU_THREADS = 1024;
 __global__ void __launch_bounds__(TAU_THREADS)
 sampler_tau_kernel(const unsigned int* __restrict__ hist, int n_sample, int* __restrict__ thr, float* __restrict__ inv_tau,
                    int* __restrict__ status) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   __shared__ float cc[HBINS], ee[HBINS];          // counts and lower edges of the occupied bins, in bin order
   __shared__ int wtot[32];
   __shared__ float fw[32];
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(SAMP_THREADS)
 sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
                        const int* __restrict__ thr, const float* __restrict__ inv_tau_p, unsigned long long* __restrict__ cand,
                        unsigned int* __restrict__ cnt, int cap) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   const int b = blockIdx.y;
   const Philox rng(*seed_ptr);
   const int T = thr[b];
@@ -375,6 +379,8 @@ template <int CAP>
 __global__ void __launch_bounds__(SEL_THREADS)
 sampler_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, int n_sample,
                       int* __restrict__ idx_out, int* __restrict__ status) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   __shared__ unsigned int hist[256];
   __shared__ uint32_t sel[4 * SEL_THREADS];
   __shared__ int ctrl[4];
@@ -423,13 +429,13 @@ int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, 
   if (vec) sampler_phist_kernel<true><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
   else sampler_phist_kernel<false><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
   MK_CUDA_CHECK(cudaGetLastError());
-  sampler_tau_kernel<<<B, TAU_THREADS, 0, st>>>(hist, n_sample, thr, inv_tau, status);
+  MK_CUDA_CHECK(launch_k(sampler_tau_kernel, dim3(B), dim3(TAU_THREADS), 0, st, hist, n_sample, thr, inv_tau, status));
   MK_CUDA_CHECK(cudaGetLastError());
-  if (vec) sampler_collect_kernel<true><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP);
-  else sampler_collect_kernel<false><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP);
+  if (vec) MK_CUDA_CHECK(launch_k(sampler_collect_kernel<true>, grid, dim3(SAMP_THREADS), 0, st, final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP));
+  else MK_CUDA_CHECK(launch_k(sampler_collect_kernel<false>, grid, dim3(SAMP_THREADS), 0, st, final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP));
   MK_CUDA_CHECK(cudaGetLastError());
   if (n_sample > 4 * SEL_THREADS) { set_last_error("NUM_SAMPLED_MATCHES %d too large", n_sample); return MK_ERR_UNSUPPORTED; }
-  sampler_select_kernel<CAND_CAP><<<(unsigned)streams, SEL_THREADS, 0, st>>>(cand, cnt, n_sample, idx_out, status);
+  MK_CUDA_CHECK(launch_k(sampler_select_kernel<CAND_CAP>, dim3((unsigned)streams), dim3(SEL_THREADS), 0, st, cand, cnt, n_sample, idx_out, status));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
@@ -451,6 +457,8 @@ __global__ void ransac_gather_kernel(const int* __restrict__ idx, const float* _
                                      const float* __restrict__ kps1, const float* __restrict__ d1,
                                      const float* __restrict__ K0, const float* __restrict__ K1, int N, int IM, int n_s,
                                      float* __restrict__ xyw) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   const int s = blockIdx.x, b = s / IM;
   __shared__ float Ki0[9], Ki1[9];
   if (threadIdx.x == 0) { inv3x3(K0 + b * 9, Ki0); inv3x3(K1 + b * 9, Ki1); }
@@ -578,6 +586,8 @@ __global__ void __launch_bounds__(HYP_THREADS)
 ransac_hyp_kernel(const float* __restrict__ xyw, const int* __restrict__ inner_idx, int IM, int IR, int n_s,
                   int hyp_per_block, float th_soft, const unsigned long long* __restrict__ seed_ptr, float* __restrict__ scores,
                   float* __restrict__ Rt, int* __restrict__ status) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   extern __shared__ float sm[];
   float* X = sm;                 // [3][n_s]
   float* Y = sm + 3 * n_s;       // [3][n_s]
@@ -713,6 +723,8 @@ ransac_finalize_kernel(const float* __restrict__ xyw, const float* __restrict__ 
                        int IM, int IR, int n_s, int n_corr, int n_ref, float th_in, const int* __restrict__ status,
                        float* __restrict__ pose, int* __restrict__ best_set, float* __restrict__ inl_mask,
                        int* __restrict__ best_hyp) {
+  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
+  pdl_trigger();
   extern __shared__ float sm[];
   float* X = sm;
   float* Y = sm + 3 * n_s;
@@ -837,7 +849,7 @@ int ransac_solve(const float* final_scores, const float* kps0, const float* d0, 
   const int IM = rp.it_matches, IR = rp.it_ransac, n_s = rp.n_sample;
   if (rp.n_corr != 3) { set_last_error("NUM_CORR_3D_3D must be 3 (got %d)", rp.n_corr); return MK_ERR_UNSUPPORTED; }
   if (n_s % HYP_THREADS) { set_last_error("NUM_SAMPLED_MATCHES must be a multiple of %d", HYP_THREADS); return MK_ERR_UNSUPPORTED; }
-  ransac_gather_kernel<<<B * IM, 256, 0, st>>>(outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, IM, n_s, xyw);
+  MK_CUDA_CHECK(launch_k(ransac_gather_kernel, dim3(B * IM), dim3(256), 0, st, outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, IM, n_s, xyw));
   MK_CUDA_CHECK(cudaGetLastError());
   const int hyp_per_block = 8;
   const size_t smem_h = (size_t)7 * n_s * 4, smem_f = (size_t)6 * n_s * 4;
@@ -848,11 +860,11 @@ int ransac_solve(const float* final_scores, const float* kps0, const float* d0, 
     attr = true;
   }
   if (smem_h > 200 * 1024) { set_last_error("NUM_SAMPLED_MATCHES too large for shared memory"); return MK_ERR_UNSUPPORTED; }
-  ransac_hyp_kernel<<<dim3(ceil_div(IR, hyp_per_block), IM, B), HYP_THREADS, smem_h, st>>>(
-      xyw, inner_idx, IM, IR, n_s, hyp_per_block, rp.th_soft, rp.seed, hyp_scores, hyp_Rt, status);
+  MK_CUDA_CHECK(launch_k(ransac_hyp_kernel, dim3(ceil_div(IR, hyp_per_block), IM, B), dim3(HYP_THREADS), smem_h, st,
+                         xyw, inner_idx, IM, IR, n_s, hyp_per_block, rp.th_soft, rp.seed, hyp_scores, hyp_Rt, status));
   MK_CUDA_CHECK(cudaGetLastError());
-  ransac_finalize_kernel<<<B, FIN_THREADS, smem_f, st>>>(xyw, hyp_scores, hyp_Rt, IM, IR, n_s, rp.n_corr, rp.n_refine,
-                                                          rp.th_inlier, status, pose, best_set, inl_mask, best_hyp);
+  MK_CUDA_CHECK(launch_k(ransac_finalize_kernel, dim3(B), dim3(FIN_THREADS), smem_f, st, xyw, hyp_scores, hyp_Rt, IM, IR, n_s, rp.n_corr,
+                         rp.n_refine, rp.th_inlier, status, pose, best_set, inl_mask, best_hyp));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
