@@ -223,6 +223,12 @@ static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorM
   return MK_OK;
 }
 
+static bool three_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_THREE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 static bool persistent_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MICKEY_GEMM_PERSISTENT"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
@@ -246,6 +252,12 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     const bool deep = ctas <= (long long)sm_count() * 5 / 4 && p.k_chunks > 3;
     if (deep) return launch_tc<BN, EPI, 6>(grid, tmA, tmB, p, stream);
+    // short-K grids of 2..3 CTAs per SM (ViT-S mlp.fc1: 372 tiles on 148 SMs) would run a second, quarter-full wave
+    // with two resident CTAs; a 2-stage ring fits three per SM and keeps the GEMM in one wave
+    if constexpr (BN == 128 && EPI == EPI_STORE_H) {
+      if (three_enabled() && p.k_chunks <= 8 && ctas > 2LL * sm_count() && ctas <= 3LL * sm_count())
+        return launch_tc<BN, EPI, 2>(grid, tmA, tmB, p, stream);
+    }
     // Persistent tile loop (accumulator double-buffered in TMEM, ring never drains) when the main loop dominates a
     // tile (K >= 768) or there are many tiles per SM.  Measured on B200: +29 % on the ViT-B GEMMs of the B=32
     // workload (523 -> 674 TFLOP/s), 1.13 PFLOP/s on a 16384x4096x4096 GEMM; but for the K=384, ~2-tiles-per-SM GEMMs

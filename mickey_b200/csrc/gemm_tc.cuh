@@ -31,7 +31,10 @@ constexpr int GEMM_THREADS = 256;
 //             latency-bound: ViT proj / fc2 at B=1 moved 64 GB/s per SM)
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  // the ring is reused as the epilogue's staging area (8 warps x 32 rows x (BN/2 + 4) floats), which a 2-stage ring
+  // does not cover
+  constexpr int ring = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2), staging = 8 * 32 * (BN / 2 + 4) * 4;
+  return (ring > staging ? ring : staging) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -203,7 +206,7 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0
 
 // ---- kernel ------------------------------------------------------------------------------------------
 template <int BN, int EPI, int GEMM_STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, (GEMM_STAGES <= 3) ? 2 : 1)
+__global__ void __launch_bounds__(GEMM_THREADS, (GEMM_STAGES <= 2) ? 3 : (GEMM_STAGES <= 3) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -212,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle-128B tiles need 1024-byte alignment
-  const uint32_t bar_base = base + GEMM_STAGES * STAGE_BYTES;   // full[S], empty[S], tmem_full, tmem_ptr
+  const uint32_t bar_base = base + gemm_smem_bytes<BN, GEMM_STAGES>() - 1024 - 256;   // full[S], empty[S], tmem_full, tmem_ptr (behind ring / staging)
   const uint32_t full_bar0 = bar_base;
   const uint32_t empty_bar0 = bar_base + 8 * GEMM_STAGES;
   const uint32_t tmem_full_bar = bar_base + 16 * GEMM_STAGES;
