@@ -297,7 +297,14 @@ def main():
     model.pipeline_depth = 1
     for _ in range(args.warmup):
         step_device()
+    ncu_range = os.environ.get("MICKEY_NCU_RANGE") == "1"     # `ncu --profile-from-start off`: capture the latency steps only
+    if ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     latency_ms = timed(step_device, args.steps, True) / args.steps
+    if ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     eng = model._engine()
     # (2) throughput: two steps in flight on alternating engines/streams (inputs are constant device tensors)
     model.pipeline_depth = max(1, args.depth)

@@ -68,24 +68,31 @@ linattn_kv_kernel(const float* __restrict__ qkv, float* __restrict__ kvout, int 
   if (vh == 0) o[256 + d] = ksum;
 }
 
-// out[i] = sum_c part[c][i] over the row chunks in a fixed order, one thread per output element.
-// grid (ceil(2176/128), G, n_img), 128 threads; 8 independent loads in flight per thread.
+// out[i] = sum_c part[c][i] over the row chunks in a fixed order: four lanes per output element each add a contiguous
+// quarter of the chunks (8 loads in flight), then the quarters are added in lane order -- the result depends only on
+// `chunks`.  grid (ceil(2176/32), G, n_img), 128 threads.
 __global__ void __launch_bounds__(128)
 linattn_kv_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int G, int chunks) {
   pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
   pdl_trigger();
   const int g = blockIdx.y, im = blockIdx.z;
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= 8 * 272) return;
-  const float* src = part + ((long long)im * G + g) * chunks * (8 * 272) + i;
+  const int i = blockIdx.x * 32 + (threadIdx.x >> 2), quarter = threadIdx.x & 3;
+  const bool live = i < 8 * 272;
+  const int per = (chunks + 3) >> 2;
+  const int c0 = quarter * per, c1 = min(chunks, c0 + per);
+  const float* src = part + ((long long)im * G + g) * chunks * (8 * 272) + (live ? i : 0);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int c = 0;
-  for (; c + 8 <= chunks; c += 8) {
+  int c = c0;
+  if (live) {
+    for (; c + 8 <= c1; c += 8) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] += src[(long long)(c + k) * (8 * 272)];
+      for (int k = 0; k < 8; ++k) acc[k] += src[(long long)(c + k) * (8 * 272)];
+    }
+    for (; c < c1; ++c) acc[0] += src[(long long)c * (8 * 272)];
   }
-  for (; c < chunks; ++c) acc[0] += src[(long long)c * (8 * 272)];
-  out[((long long)im * G + g) * (8 * 272) + i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  float v = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  const float v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2), v3 = __shfl_down_sync(0xffffffffu, v, 3);
+  if (live && quarter == 0) out[((long long)im * G + g) * (8 * 272) + i] = (v + v1) + (v2 + v3);
 }
 
 // Linear attention, query half (attention.py:52,60-61): msg = (Q KV) / (Q . Ksum + eps) * L, Q = elu(q)+1.
@@ -95,7 +102,9 @@ linattn_msg_kernel(const float* __restrict__ qkv, const float* __restrict__ kv, 
                    int w2, float eps) {
   pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
   pdl_trigger();
-  __shared__ float KVs[8][272];
+  // a warp reads KVs[head][..] for its 8 heads at once (4 positions share each address): a row stride of 272 floats
+  // puts heads 0/2/4/6 in the same bank (4-way conflict on all 272 reads per thread); 276 = 4 mod 32 spreads them
+  __shared__ float KVs[8][276];
   const int g = blockIdx.y, im = blockIdx.z, t = threadIdx.x;
   const int per_img = h2 * w2;
   const float len = (float)((h2 - 2) * (w2 - 2));
@@ -141,7 +150,7 @@ int linattn_kv(const float* qkv, float* kv_part, float* kv, int n_img, int G, in
   const int chunks = linattn_kv_chunks(h2, w2);
   MK_CUDA_CHECK(launch_k(linattn_kv_kernel, dim3(chunks, G, n_img), dim3(256), 0, s, qkv, kv_part, G, h2, w2));
   MK_CUDA_CHECK(cudaGetLastError());
-  MK_CUDA_CHECK(launch_k(linattn_kv_reduce_kernel, dim3(ceil_div(8 * 272, 128), G, n_img), dim3(128), 0, s, kv_part, kv, G, chunks));
+  MK_CUDA_CHECK(launch_k(linattn_kv_reduce_kernel, dim3(ceil_div(8 * 272, 32), G, n_img), dim3(128), 0, s, kv_part, kv, G, chunks));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
