@@ -464,7 +464,7 @@ __global__ void ransac_gather_kernel(const int* __restrict__ idx, const float* _
   if (threadIdx.x == 0) { inv3x3(K0 + b * 9, Ki0); inv3x3(K1 + b * 9, Ki1); }
   __syncthreads();
   float* o = xyw + (long long)s * 8 * n_s;
-  for (int i = threadIdx.x; i < n_s; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n_s; i += gridDim.y * blockDim.x) {   // one sample per thread
     const int cell = idx[(long long)s * n_s + i];
     const int i0 = cell / N, i1 = cell - i0 * N;
     const float u0 = kps0[((long long)b * 2 + 0) * N + i0], v0 = kps0[((long long)b * 2 + 1) * N + i0];
@@ -849,7 +849,7 @@ int ransac_solve(const float* final_scores, const float* kps0, const float* d0, 
   const int IM = rp.it_matches, IR = rp.it_ransac, n_s = rp.n_sample;
   if (rp.n_corr != 3) { set_last_error("NUM_CORR_3D_3D must be 3 (got %d)", rp.n_corr); return MK_ERR_UNSUPPORTED; }
   if (n_s % HYP_THREADS) { set_last_error("NUM_SAMPLED_MATCHES must be a multiple of %d", HYP_THREADS); return MK_ERR_UNSUPPORTED; }
-  MK_CUDA_CHECK(launch_k(ransac_gather_kernel, dim3(B * IM), dim3(256), 0, st, outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, IM, n_s, xyw));
+  MK_CUDA_CHECK(launch_k(ransac_gather_kernel, dim3(B * IM, ceil_div(n_s, 256)), dim3(256), 0, st, outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, IM, n_s, xyw));
   MK_CUDA_CHECK(cudaGetLastError());
   const int hyp_per_block = 8;
   const size_t smem_h = (size_t)7 * n_s * 4, smem_f = (size_t)6 * n_s * 4;
