@@ -381,6 +381,23 @@ def main():
         return None
 
     dominant = max(prof, key=lambda k: prof[k]["ms_per_step"]) if prof else None
+
+    def attention_roof():
+        """The tensor roofline object plus the bound that head_dim 64 really imposes: one MUFU.EX2 per logit at 16 per
+        clock per SM (measured, tools/ubench/pipe_rates.cu) costs twice the tile's MMA time."""
+        r = roof("vit.attention")
+        if r is None:
+            return None
+        D_, depth_ = VIT_DIMS[VARIANT]
+        T_ = (H_IMG // 14) * (W_IMG // 14) + 1
+        exps = depth_ * 2 * B * (D_ // 64) * T_ * (-(-T_ // 128) * 128)           # padded key tiles are exponentiated too
+        sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+        rate = exps / (prof["vit.attention"]["ms_per_step"] / 1e3) / (sm_mhz * 1e6) / n_sm
+        r["mufu"] = {"achieved": rate, "peak": 16.0, "unit": "exp2/clk/SM", "frac": rate / 16.0,
+                     "note": "head_dim 64: 1024 MUFU clk vs 512 tensor clk per 128x128 tile, so 16 exp2/clk/SM caps the kernel at "
+                             "half of the tensor peak"}
+        return r
     vit_gemm_ms = sum(prof[k]["ms_per_step"] for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2") if k in prof)
     vit_gemm_fl = sum(flops[k] for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2"))
     line = {
@@ -398,12 +415,12 @@ def main():
                 "h2d_bytes_per_step": int(2 * B * 3 * H_IMG * W_IMG * 4), "d2h_bytes_per_step": int(B * 13 * 4)},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": roof(dominant) if dominant else None,
+        "roofline": (attention_roof() if dominant == "vit.attention" else roof(dominant)) if dominant else None,
         "roofline_vit_gemm": ({"kernel": "vit.qkv+proj+fc1+fc2", "bound": "tensor", "achieved": vit_gemm_fl / (vit_gemm_ms / 1e3) / 1e12,
                                "peak": peaks["tflops"], "unit": "TFLOP/s",
                                "frac": vit_gemm_fl / (vit_gemm_ms / 1e3) / 1e12 / peaks["tflops"], "traffic": None}
                               if vit_gemm_ms > 0 else None),
-        "roofline_attention": roof("vit.attention"), "roofline_head_conv": roof("head.conv3x3"),
+        "roofline_attention": attention_roof(), "roofline_head_conv": roof("head.conv3x3"),
         "roofline_matcher": roof("match.dual_softmax"), "roofline_sampler": roof("solve.sample_outer"),
         "stage_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
     }

@@ -115,7 +115,8 @@ int mk_profile_read(mk_handle* h, char* buf, int buf_bytes);
 
 /* ---- operator-level entry points (unit tests of single kernels; not needed by an integrator) ---- */
 typedef struct mk_gemm_args {
-  int epi;                 /* 0 STORE_H, 1 RESID_F, 2 PATCH, 3 CONV, 4 STORE_F, 5 LN, 6 LSE, 7 DUAL */
+  int epi;                 /* 0 STORE_H, 1 RESID_F, 2 PATCH, 3 CONV, 4 STORE_F, 5 LN, 6 LSE, 7 DUAL,
+                              8 RESID_LN (RESID_F, then out_h = LayerNorm(out_f row) * aux + beta; N <= 1024) */
   int impl;                /* 0 default (tcgen05), 1 tcgen05, 2 SIMT debug kernel */
   const void* a; long long a_rows, a_cols, a_ld;
   const void* b; long long b_rows, b_cols, b_ld;

@@ -171,6 +171,88 @@ template <int CPL> __device__ __forceinline__ void ld_h(const __half* p, float (
   else { v[0] = __half2float(*p); }
 }
 
+// ---- fused residual + LayerNorm epilogue (EPI_RESID_LN) -------------------------------------------------
+// A warp owns 32 rows x 64 columns of the tile (lane = column pair).  Row statistics are needed per ROW, the
+// layout is per COLUMN: every lane first accumulates its own partial of all 32 rows, then a recursive-halving
+// exchange (31 shuffles instead of 32 x 5) leaves the total of row r in lane r.  The order of the additions is fixed.
+__device__ __forceinline__ float warp_rowsum32(float (&part)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = upper ? part[i] : part[i + o];
+      const float keep = upper ? part[i + o] : part[i];
+      part[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return part[0];
+}
+
+// pass 1: x = out_f + gamma * (acc + bias) -> out_f (fp32, in place) and back into the staging block; returns the
+// sum of row (lane) over the warp's 64 columns.  Rows at or beyond p.M contribute zeros and are not stored.
+__device__ __forceinline__ float resid_ln_pass1(const GemmParams& p, int row0, int lane, int col_base, float* stage) {
+  constexpr int LDS = 64 + 4, RB = 8;
+  const int col = col_base + lane * 2;
+  const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + col)), gam = __ldg(reinterpret_cast<const float2*>(p.gamma + col));
+  const int rows = min(32, p.M - row0);
+  float part[32];
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += RB) {
+    float2 v[RB], x[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = r0 + i;
+      v[i] = *reinterpret_cast<const float2*>(stage + r * LDS + lane * 2);
+      x[i] = make_float2(0.f, 0.f);
+      if (r < rows) x[i] = *reinterpret_cast<const float2*>(p.out_f + (size_t)(row0 + r) * p.out_f_ld + col);
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = r0 + i;
+      float2 y = make_float2(0.f, 0.f);
+      if (r < rows) {
+        y.x = fmaf(gam.x, v[i].x + bias.x, x[i].x); y.y = fmaf(gam.y, v[i].y + bias.y, x[i].y);
+        *reinterpret_cast<float2*>(p.out_f + (size_t)(row0 + r) * p.out_f_ld + col) = y;
+      }
+      *reinterpret_cast<float2*>(stage + r * LDS + lane * 2) = y;
+      part[r] = y.x + y.y;
+    }
+  }
+  return warp_rowsum32(part, lane);
+}
+
+// pass 2: sum over the warp's 64 columns of (x - mean_row)^2; mean_l holds the mean of row (lane)
+__device__ __forceinline__ float resid_ln_pass2(int lane, const float* stage, float mean_l) {
+  constexpr int LDS = 64 + 4;
+  float part[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const float2 x = *reinterpret_cast<const float2*>(stage + r * LDS + lane * 2);
+    const float mean = __shfl_sync(0xffffffffu, mean_l, r);
+    const float d0 = x.x - mean, d1 = x.y - mean;
+    part[r] = d0 * d0 + d1 * d1;
+  }
+  return warp_rowsum32(part, lane);
+}
+
+// pass 3: out_h = (x - mean) * rstd * ln_w + ln_b   (ln_w = p.aux, ln_b = p.beta)
+__device__ __forceinline__ void resid_ln_pass3(const GemmParams& p, int row0, int lane, int col_base, const float* stage,
+                                               float mean_l, float rstd_l) {
+  constexpr int LDS = 64 + 4;
+  const int col = col_base + lane * 2;
+  const float2 w = __ldg(reinterpret_cast<const float2*>(p.aux + col)), b = __ldg(reinterpret_cast<const float2*>(p.beta + col));
+  const int rows = min(32, p.M - row0);
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const float2 x = *reinterpret_cast<const float2*>(stage + r * LDS + lane * 2);
+    const float mean = __shfl_sync(0xffffffffu, mean_l, r), rstd = __shfl_sync(0xffffffffu, rstd_l, r);
+    if (r < rows)
+      *reinterpret_cast<__half2*>(p.out_h + (size_t)(row0 + r) * p.out_h_ld + col) =
+          __floats2half2_rn((x.x - mean) * rstd * w.x + b.x, (x.y - mean) * rstd * w.y + b.y);
+  }
+}
+
 template <int EPI, int W>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int row0, int lane, int col_base,
                                               const float* __restrict__ stage, float mean_l, float rstd_l) {

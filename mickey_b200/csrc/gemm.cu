@@ -195,6 +195,28 @@ static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return MK_OK;
 }
 
+// EPI_RESID_LN: the grid.y CTAs of a row of tiles form one thread-block cluster (row statistics through DSMEM)
+template <int BN, int EPI, int STAGES>
+static int launch_tc_cluster(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  if (!attr_set) {
+    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = grid.y; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, STAGES>, tmA, tmB, p));
+  return MK_OK;
+}
+
 static bool wide_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MICKEY_GEMM_WIDE"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
@@ -238,7 +260,11 @@ static bool persistent_enabled() {
 template <int BN, int EPI>
 static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmParams& p, cudaStream_t stream, int impl) {
   dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(p.N, BN), p.groups);
+  if constexpr (EPI == EPI_RESID_LN) {
+    if (impl == GEMM_IMPL_SIMT || BN != 128 || grid.y > 8 || grid.z != 1) { set_last_error("EPI_RESID_LN: tcgen05 path, N <= 1024, one group"); return MK_ERR_UNSUPPORTED; }
+  }
   if (impl == GEMM_IMPL_SIMT) {
+    if constexpr (EPI != EPI_RESID_LN)
     MK_CUDA_CHECK(launch_k(gemm_simt_kernel<BN, EPI>, grid, dim3(128), 0, stream, reinterpret_cast<const __half*>(A.ptr),
                            (long long)A.rows, (long long)A.ld, reinterpret_cast<const __half*>(B.ptr), (long long)B.rows,
                            (long long)B.ld, p));
@@ -251,6 +277,13 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
     // grids that give every SM at most ~one CTA run the deep ring; bigger grids keep two CTAs per SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     const bool deep = ctas <= (long long)sm_count() * 5 / 4 && p.k_chunks > 3;
+    if constexpr (EPI == EPI_RESID_LN) {       // one-tile kernels only (every warp of the CTA takes part in the cluster barriers)
+      if constexpr (BN == 128) {
+        if (deep) return launch_tc_cluster<BN, EPI, 6>(grid, tmA, tmB, p, stream);
+        return launch_tc_cluster<BN, EPI, 3>(grid, tmA, tmB, p, stream);
+      }
+      return MK_ERR_UNSUPPORTED;
+    }
     if (deep) return launch_tc<BN, EPI, 6>(grid, tmA, tmB, p, stream);
     // short-K grids of 2..3 CTAs per SM (ViT-S mlp.fc1: 372 tiles on 148 SMs) would run a second, quarter-full wave
     // with two resident CTAs; a 2-stage ring fits three per SM and keeps the GEMM in one wave
@@ -289,6 +322,21 @@ static int launch_bn(int bn, const GemmOperand& A, const GemmOperand& B, const G
   return MK_ERR_INVALID;
 }
 
+// Would launch_gemm run a [M, N] x K RESID_F GEMM on a one-tile kernel (so that LayerNorm can be fused into it)?
+bool gemm_resid_ln_supported(int M, int N, int k_chunks) {
+  // opt-in (MICKEY_FUSE_LN=1).  Measured on the C2 workload: the fused epilogue removes 23 LayerNorm launches (4.8 us each)
+  // but its three cluster barriers and two extra passes over the staged tile cost attn.proj / mlp.fc2 +5.5 us each:
+  // 1.852 vs 1.808 ms per step, 754 vs 798 pairs/s (profiles/r01_notes.md).  Kept for the next round (single-exchange
+  // statistics, push instead of pull).
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MICKEY_FUSE_LN"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (!on || use_simt() || N % 128 || N > 1024) return false;
+  const long long ctas = (long long)ceil_div(M, BLOCK_M) * (N / 128);
+  const bool deep = ctas <= (long long)sm_count() * 5 / 4 && k_chunks > 3;
+  if (deep) return true;
+  return !(persistent_enabled() && (k_chunks >= 12 || ctas >= 4LL * sm_count()));
+}
+
 int launch_gemm(int epi, const GemmOperand& A, const GemmOperand& B, const GemmParams& p, cudaStream_t stream, int impl) {
   if (impl == GEMM_IMPL_DEFAULT) impl = use_simt() ? GEMM_IMPL_SIMT : GEMM_IMPL_TC;
   if (p.k_chunks <= 0 || p.M <= 0 || p.N <= 0 || p.groups <= 0) { set_last_error("bad GEMM shape"); return MK_ERR_INVALID; }
@@ -297,9 +345,14 @@ int launch_gemm(int epi, const GemmOperand& A, const GemmOperand& B, const GemmP
   int bn = (matcher || p.N % 128 == 0) ? 128 : 64;
   if (!matcher && p.N % bn) { set_last_error("GEMM N=%d not tileable", p.N); return MK_ERR_INVALID; }
   if (epi == EPI_LN && p.N != 128) { set_last_error("EPI_LN needs N == 128"); return MK_ERR_INVALID; }
+  if (epi == EPI_RESID_LN && (p.N % 128 || p.N > 1024 || p.groups != 1 || !p.aux || !p.beta || !p.out_h || !p.out_f)) {
+    set_last_error("EPI_RESID_LN needs N % 128 == 0, N <= 1024, one group, LN weight (aux), LN bias (beta), out_f and out_h");
+    return MK_ERR_INVALID;
+  }
   switch (epi) {
     case EPI_STORE_H: return launch_bn<EPI_STORE_H>(bn, A, B, p, stream, impl);
     case EPI_RESID_F: return launch_bn<EPI_RESID_F>(bn, A, B, p, stream, impl);
+    case EPI_RESID_LN: return launch_one<128, EPI_RESID_LN>(A, B, p, stream, impl);
     case EPI_PATCH:   return launch_bn<EPI_PATCH>(bn, A, B, p, stream, impl);
     case EPI_CONV:    return launch_bn<EPI_CONV>(bn, A, B, p, stream, impl);
     case EPI_STORE_F: return launch_bn<EPI_STORE_F>(bn, A, B, p, stream, impl);

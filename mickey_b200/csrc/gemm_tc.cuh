@@ -34,7 +34,8 @@ constexpr int gemm_smem_bytes() {
   // the ring is reused as the epilogue's staging area (8 warps x 32 rows x (BN/2 + 4) floats), which a 2-stage ring
   // does not cover
   constexpr int ring = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2), staging = 8 * 32 * (BN / 2 + 4) * 4;
-  return (ring > staging ? ring : staging) + 1024 /*align slack*/ + 256 /*barriers*/;
+  // + row statistics of EPI_RESID_LN (never run on the 2-stage ring, whose three CTAs per SM have no room to spare)
+  return (ring > staging ? ring : staging) + 1024 /*align slack*/ + 256 /*barriers*/ + (STAGES == 2 ? 0 : 2048);
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -122,6 +123,23 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_f16() {
   return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// ---- thread-block cluster helpers (EPI_RESID_LN) -------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {     // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
 // ---- tile epilogue -----------------------------------------------------------------------------------
 // One warp's share of a 128 x BN accumulator tile: TMEM lanes 32q..32q+31 (its quadrant q) and half of the tile's
 // 32-column chunks (warps q and q+4 split the columns).  `stage` is the warp's private 32 x (BN/2 + 4) fp32
@@ -129,7 +147,8 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_f16() {
 // kernel hands the TMEM buffer back to the MMA warp there, before the global stores).
 template <int BN, int EPI, typename Release>
 __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0, int n0, int n_tile, int q, int half,
-                                              int lane, uint32_t tmem_acc, float* stage, Release release) {
+                                              int lane, uint32_t tmem_acc, float* stage, Release release,
+                                              float* red = nullptr, uint32_t red_saddr = 0) {
   constexpr int CHUNKS = BN / 32;
   constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
   constexpr int W = BN / 2;                      // columns owned by this warp
@@ -164,6 +183,36 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0
     release();
     __syncwarp();
     epilogue_rows<EPI_LN, W>(p, g, m0 + q * 32, lane, n0 + half * W, stage, mean, rstd);
+  } else if constexpr (EPI == EPI_RESID_LN) {
+    // `red` = this CTA's float[2 statistics][2 column halves][128 rows]; the CTAs of the cluster hold the other
+    // 128-column tiles of the same rows
+    static_assert(BN == 128, "EPI_RESID_LN: 128-wide tiles");
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      tmem_ld32(taddr + (c_begin + cc) * 32, v);
+      float4* dst = reinterpret_cast<float4*>(stage + lane * (64 + 4) + cc * 32);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) dst[k4] = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+    }
+    release();
+    __syncwarp();
+    const int row0 = m0 + q * 32, col_base = n0 + half * 64, slot = half * 128 + q * 32 + lane;
+    const uint32_t n_cta = cluster_size();
+    const float inv_n = 1.0f / (float)p.N;
+    red[slot] = resid_ln_pass1(p, row0, lane, col_base, stage);
+    cluster_sync_all();
+    float tot = 0.f;
+    for (uint32_t c = 0; c < n_cta; ++c)
+      tot += ld_dsmem_f32(red_saddr + (q * 32 + lane) * 4, c) + ld_dsmem_f32(red_saddr + (128 + q * 32 + lane) * 4, c);
+    const float mean = tot * inv_n;
+    red[256 + slot] = resid_ln_pass2(lane, stage, mean);
+    cluster_sync_all();
+    float tot2 = 0.f;
+    for (uint32_t c = 0; c < n_cta; ++c)
+      tot2 += ld_dsmem_f32(red_saddr + (256 + q * 32 + lane) * 4, c) + ld_dsmem_f32(red_saddr + (384 + q * 32 + lane) * 4, c);
+    const float rstd = rsqrtf(tot2 * inv_n + p.eps);
+    resid_ln_pass3(p, row0, lane, col_base, stage, mean, rstd);
+    cluster_sync_all();                  // no CTA may exit while a peer can still read its statistics
   } else if constexpr (EPI == EPI_LSE) {
     float s = 0.f;
     for (int c = c_begin; c < c_end; ++c) {
@@ -215,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle-128B tiles need 1024-byte alignment
-  const uint32_t bar_base = base + gemm_smem_bytes<BN, GEMM_STAGES>() - 1024 - 256;   // full[S], empty[S], tmem_full, tmem_ptr (behind ring / staging)
+  const uint32_t bar_base = base + gemm_smem_bytes<BN, GEMM_STAGES>() - 1024 - 256 - (GEMM_STAGES == 2 ? 0 : 2048);   // full[S], empty[S], tmem_full, tmem_ptr (behind ring / staging)
   const uint32_t full_bar0 = bar_base;
   const uint32_t empty_bar0 = bar_base + 8 * GEMM_STAGES;
   const uint32_t tmem_full_bar = bar_base + 16 * GEMM_STAGES;
@@ -304,7 +353,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   pdl_trigger();                 // main loop done: the next kernel's CTAs may start their prologue under our epilogue
   tile_epilogue<BN, EPI>(p, g, m0, n0, (int)blockIdx.y, warp & 3, warp >> 2, lane, tmem_base,
-                         reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * (BN / 2 + 4)), [] {});
+                         reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * (BN / 2 + 4)), [] {},
+                         reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)), bar_base + 256);
 
   tc_fence_before();
   __syncthreads();

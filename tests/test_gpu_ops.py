@@ -278,6 +278,34 @@ def test_matcher_epilogues_vs_dual_softmax(impl, B, N):
     assert rel_err(fin, ref * s0[:, :, None].double() * s1[:, None, :].double()) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(3878, 384, 384),      # ViT-S attn.proj at 720x540: 31 x 3 tiles, deep ring, clusters of 3
+                                   (3878, 384, 1536),     # ViT-S mlp.fc2
+                                   (1000, 768, 768),      # clusters of 6
+                                   (20000, 384, 384),     # 157 x 3 tiles: 3-stage ring, two CTAs per SM
+                                   (700, 1024, 256),      # clusters of 8
+                                   (130, 128, 128)])      # a cluster of one, ragged last row tile
+def test_gemm_residual_layernorm_fused(M, N, K):
+    """EPI_RESID_LN: x += gamma * (a w^T + bias) in fp32, then LayerNorm(x) * ln_w + ln_b in fp16 from the same epilogue;
+    the row statistics cross the N/128 CTAs of a thread-block cluster through distributed shared memory."""
+    a, w = _rand(M, K, seed=60).half(), _rand(N, K, scale=0.05, seed=61).half()
+    bias, gamma, x = _rand(N, scale=0.1, seed=62), _rand(N, seed=63), _rand(M, N, seed=64)
+    ln_w, ln_b = _rand(N, seed=65), _rand(N, scale=0.3, seed=66)
+    x_ref = x + gamma * (a.float() @ w.float().t() + bias)
+    ln_ref = F.layer_norm(x_ref, (N,), ln_w, ln_b, eps=1e-6)
+    out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+    gemm("RESID_LN", a, w, M, N, K, bias=bias, gamma=gamma, out_f=x, out_f_ld=N, aux=ln_w, beta=ln_b, out_h=out, out_h_ld=N, eps=1e-6)
+    torch.cuda.synchronize()
+    assert rel_err(x, x_ref) < 1e-5
+    assert rel_err(out, ln_ref) < 1e-3        # fp16 output rounding
+    # same statistics as the stand-alone LayerNorm kernel on the updated residual
+    lib = _lib.load()
+    if N in (384, 768, 1024):
+        out2 = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+        _lib.check(lib.mk_op_layernorm(_lib.ptr(x), _lib.ptr(ln_w), _lib.ptr(ln_b), _lib.ptr(out2), M, N, 1e-6, 0, 0, 0, stream()))
+        torch.cuda.synchronize()
+        assert (out.float() - out2.float()).abs().max() <= 2e-2 * ln_ref.abs().max()
+
+
 def _philox4x32_7(c0, c1, c2, c3, seed):
     """numpy restatement of the device generator (ransac.cu Philox): counters are uint32 arrays."""
     import numpy as np
