@@ -223,6 +223,12 @@ static bool wide_enabled() {
   return v == 1;
 }
 
+static int wide_min_pct() {   // 128 x 256 tiles when at least this many (in % of the SM count) remain; MICKEY_GEMM_WIDE_MIN_PCT
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_WIDE_MIN_PCT"); v = e ? atoi(e) : 200; if (v <= 0) v = 200; }
+  return v;
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -299,7 +305,7 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
       // 128 x 256 tiles (one N=256 UMMA per K step, A tile re-read half as often: 85 instead of 64 flop per byte of
       // L2 traffic, which is what bounds the 128 x 128 tiling) when N allows and enough tiles remain
       if constexpr (BN == 128 && (EPI == EPI_STORE_H || EPI == EPI_RESID_F || EPI == EPI_CONV || EPI == EPI_STORE_F)) {
-        if (wide_enabled() && p.N % 256 == 0 && ctas / 2 >= 2LL * sm_count()) {
+        if (wide_enabled() && p.N % 256 == 0 && (ctas / 2) * 100 >= (long long)wide_min_pct() * sm_count()) {
           CUtensorMap tmB2;
           rc = make_tensor_map_f16(&tmB2, B.ptr, B.rows, B.cols, B.ld, 256);
           if (rc) return rc;
