@@ -395,8 +395,8 @@ def main():
         n_sm = torch.cuda.get_device_properties(0).multi_processor_count
         rate = exps / (prof["vit.attention"]["ms_per_step"] / 1e3) / (sm_mhz * 1e6) / n_sm
         r["mufu"] = {"achieved": rate, "peak": 16.0, "unit": "exp2/clk/SM", "frac": rate / 16.0,
-                     "note": "head_dim 64: 1024 MUFU clk vs 512 tensor clk per 128x128 tile, so 16 exp2/clk/SM caps the kernel at "
-                             "half of the tensor peak"}
+                     "note": "head_dim 64: 1024 MUFU clk vs 512 tensor clk per 128x128 tile, so 16 exp2/clk/SM caps a kernel that sends "
+                             "every exp2 to the MUFU at half of the tensor peak; this one evaluates a quarter of them on the FMA pipe"}
         return r
     vit_gemm_ms = sum(prof[k]["ms_per_step"] for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2") if k in prof)
     vit_gemm_fl = sum(flops[k] for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2"))

@@ -55,6 +55,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; a degree-4 polynomial for 2^f
+// (|rel err| < 5e-5, far below the fp16 rounding of P) and n added into the exponent field.  Used for a fraction of
+// the logits so that the MUFU, which bounds this kernel, sees fewer of them.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -79,6 +92,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
+template <int POLY>     // every POLY-th pair of logits takes the FMA-pipe exp2 (0: none)
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int D, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -229,7 +243,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float p0 = ex2_approx(fmaf(s[2 * i], scale_log2, neg_m)), p1 = ex2_approx(fmaf(s[2 * i + 1], scale_log2, neg_m));
+        const float x0 = fmaf(s[2 * i], scale_log2, neg_m), x1 = fmaf(s[2 * i + 1], scale_log2, neg_m);
+        const bool poly = (POLY > 0) && (i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1);   // compile-time after unrolling
+        const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
         sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1;
         __half2 h = __floats2half2_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&h);
@@ -285,8 +301,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
 int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s) {
   if (D != heads * FA_D) { set_last_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads); return MK_ERR_UNSUPPORTED; }
   static bool attr = false;
+  static int poly = 0;
   if (!attr) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    // default: every 4th pair (25 %) on the FMA pipe -- measured 32.0 -> 29.9 us (one 720x540 pair) and 1156 -> 1100 us
+    // (64 images, ViT-B); 12.5 % gives half of that, 50 % is slower than none (issue-bound).  MICKEY_ATTN_POLY=0 disables.
+    const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : 4;
     attr = true;
   }
   CUtensorMap tm;
@@ -294,7 +317,8 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   if (rc) return rc;
   dim3 grid(ceil_div(T, FA_BQ), heads, n_img);
   const float scale_log2 = 0.125f * 1.4426950408889634f;
-  MK_CUDA_CHECK(launch_k(attention_tc_kernel, grid, dim3(FA_THREADS), (size_t)FA_SMEM, s, tm, (__half*)out, T, D, scale_log2));
+  auto kern = poly == 8 ? attention_tc_kernel<8> : poly == 4 ? attention_tc_kernel<4> : poly == 3 ? attention_tc_kernel<3> : attention_tc_kernel<0>;
+  MK_CUDA_CHECK(launch_k(kern, grid, dim3(FA_THREADS), (size_t)FA_SMEM, s, tm, (__half*)out, T, D, scale_log2));
   return MK_OK;
 }
 
