@@ -306,7 +306,6 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     // default: every 4th pair (25 %) on the FMA pipe -- measured 32.0 -> 29.9 us (one 720x540 pair) and 1156 -> 1100 us
     // (64 images, ViT-B); 12.5 % gives half of that, 50 % is slower than none (issue-bound).  MICKEY_ATTN_POLY=0 disables.
     const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : 4;
@@ -317,7 +316,7 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   if (rc) return rc;
   dim3 grid(ceil_div(T, FA_BQ), heads, n_img);
   const float scale_log2 = 0.125f * 1.4426950408889634f;
-  auto kern = poly == 8 ? attention_tc_kernel<8> : poly == 4 ? attention_tc_kernel<4> : poly == 3 ? attention_tc_kernel<3> : attention_tc_kernel<0>;
+  auto kern = poly == 8 ? attention_tc_kernel<8> : poly == 4 ? attention_tc_kernel<4> : attention_tc_kernel<0>;
   MK_CUDA_CHECK(launch_k(kern, grid, dim3(FA_THREADS), (size_t)FA_SMEM, s, tm, (__half*)out, T, D, scale_log2));
   return MK_OK;
 }
