@@ -16,6 +16,9 @@ GOLDEN_CASES = {
                        weight_seed=0, data_seed=5, rng_seed=3, stride=1),
     "vitb_small": dict(variant="vitb", it_matches=2, it_ransac=8, batch=1, height=224, width=182,
                        weight_seed=1, data_seed=6, rng_seed=4, stride=1),
+    # the reference's default backbone (ViT-L/14: 24 blocks, 16 heads, D = 1024); 15x13 grid: N = 195, N*N odd
+    "vitl_small": dict(variant="vitl", it_matches=2, it_ransac=8, batch=1, height=210, width=182,
+                       weight_seed=2, data_seed=8, rng_seed=5, stride=1),
     # BASELINE config 2 at full size (N=1938): N x N tensors stored with stride 17
     "vits_720x540": dict(variant="vits", it_matches=8, it_ransac=64, batch=1, height=720, width=540,
                          weight_seed=0, data_seed=7, rng_seed=11, stride=17),

@@ -51,7 +51,7 @@ def _to_dev(d):
     return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in d.items()}
 
 
-@pytest.mark.parametrize("name", ["vits_small", "vitb_small", "vits_720x540"])
+@pytest.mark.parametrize("name", ["vits_small", "vitb_small", "vitl_small", "vits_720x540"])
 def test_extract_and_match_vs_reference_golden(name):
     spec, gold = GOLDEN_CASES[name], load_golden(name)
     cfg, model = _model(spec["variant"], spec["it_matches"], spec["it_ransac"], spec["weight_seed"])
