@@ -251,6 +251,37 @@ static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorM
   return MK_OK;
 }
 
+// opt-in: cta_group::2 kernel (256 x 256 tiles over a CTA pair), not yet validated on hardware
+static bool two_sm_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_2SM"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+
+template <int EPI>
+static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  constexpr int smem = gemm_2sm_smem_bytes();
+  if (!attr_set) {
+    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long long total = (long long)tiles256.x * tiles256.y * tiles256.z;
+  const long long pairs = sm_count() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs))); cfg.blockDim = dim3(PERSIST_THREADS);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI>, tmA, tmB, p, (int)tiles256.x, (int)tiles256.y));
+  return MK_OK;
+}
+
 static bool three_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MICKEY_GEMM_THREE"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -305,6 +336,8 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
       // 128 x 256 tiles (one N=256 UMMA per K step, A tile re-read half as often: 85 instead of 64 flop per byte of
       // L2 traffic, which is what bounds the 128 x 128 tiling) when N allows and enough tiles remain
       if constexpr (BN == 128 && (EPI == EPI_STORE_H || EPI == EPI_RESID_F || EPI == EPI_CONV || EPI == EPI_STORE_F)) {
+        if (two_sm_enabled() && p.N % 256 == 0)      // tmB's 128-row box is exactly one CTA's half of the 256 B rows
+          return launch_2sm<EPI>(dim3(ceil_div(p.M, 256), p.N / 256, grid.z), tmA, tmB, p, stream);
         if (wide_enabled() && p.N % 256 == 0 && (ctas / 2) * 100 >= (long long)wide_min_pct() * sm_count()) {
           CUtensorMap tmB2;
           rc = make_tensor_map_f16(&tmB2, B.ptr, B.rows, B.cols, B.ld, 256);

@@ -508,4 +508,185 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
 }
 
+// ---- 2-SM persistent kernel (cta_group::2) ----------------------------------------------------------------
+// STATUS: written at the end of round 1 after the GPU budget was spent -- compiles for sm_100a, NOT yet executed on
+// hardware, opt-in (MICKEY_GEMM_2SM=1), not covered by the default test run.
+// Rationale (profiles/r01_notes.md): the big GEMMs sit on the chip's L2->SM operand throughput, not on the tensor
+// pipe: a 128 x 256 tile loads 48 KB per 64-deep K step (85 flop per byte).  Here a CTA PAIR (cluster of 2 on one
+// TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA loads its 128 rows of A and its 128 rows of
+// B (32 KB per K step for 128 x 256 outputs: 128 flop per byte), the leader CTA issues one M=256, N=256 UMMA per
+// 16-deep K slice that reads both CTAs' shared memory, and each CTA keeps its 128 accumulator rows in its own TMEM
+// (2 x 256 columns, double-buffered across tiles).  Barriers: `full` lives in the leader (both CTAs' TMA loads
+// complete_tx on it: peer bit of the mbarrier address cleared), `empty` / `tmem_full` are signalled in both CTAs by a
+// multicast tcgen05.commit, `tmem_empty` lives in the leader and collects the 8 epilogue warps of both CTAs (the peer
+// arrives remotely).  Warp roles as in the 1-SM persistent kernel; the peer's MMA warp idles.
+constexpr int TWO_SM_STAGES = 4;
+constexpr int gemm_2sm_smem_bytes() {
+  return TWO_SM_STAGES * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 8 * 32 * (64 + 4) * 4 + 1024 + 256;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (same offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have retired
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrive on the mbarrier at `local_bar`'s offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmParams p, const int tiles_m, const int tiles_n) {
+  // tiles_m = ceil(M / 256), tiles_n = N / 256; cluster c = blockIdx.x / 2 walks tiles c, c + gridDim.x / 2, ...
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int BN = 256;
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                    // this CTA's 128 rows of A
+  constexpr int B_BYTES = 128 * BLOCK_K * 2;                        // this CTA's 128 rows (N half) of B
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGING_BYTES = 8 * 32 * (64 + 4) * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t staging = base + TWO_SM_STAGES * STAGE_BYTES;
+  const uint32_t bar_base = staging + STAGING_BYTES;
+  const uint32_t full_bar0 = bar_base;
+  const uint32_t empty_bar0 = bar_base + 8 * TWO_SM_STAGES;
+  const uint32_t tfull_bar0 = bar_base + 16 * TWO_SM_STAGES;        // [2]
+  const uint32_t tempty_bar0 = tfull_bar0 + 16;                     // [2], used in the leader only
+  const uint32_t tmem_ptr_addr = tempty_bar0 + 16;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                          // 0 = leader
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int tiles_per_group = tiles_m * tiles_n;
+  const int total = tiles_per_group * p.groups;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TWO_SM_STAGES; ++s) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar0 + 8 * a, 1); mbar_init(tempty_bar0 + 8 * a, 16); }   // 8 warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {     // both CTAs, same warp id, same destination offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                               // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of A, own 128 rows of B; bytes credited to the leader's barrier =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total; t += n_clusters) {
+        const int g = t / tiles_per_group, r = t - g * tiles_per_group;
+        const int m0 = (r / tiles_n) * 256 + (int)rank * 128, n0 = (r % tiles_n) * BN + (int)rank * 128;
+        const int a_col0 = p.a_col_base + g * p.a_col_group_off;
+        const int a_row0 = m0 + g * p.a_row_group_off;
+        const int b_row0 = n0 + g * p.b_row_group_off;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int tap = kc / p.chunks_per_tap;
+          const int kin = kc - tap * p.chunks_per_tap;
+          mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);             // local: the multicast commit frees the stage in both CTAs
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint32_t fb = full_bar0 + 8 * stage;
+          if (rank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES);       // the pair's four loads of this stage
+          tma_load_2d_2sm(sa, &tmA, fb, a_col0 + kin * BLOCK_K, a_row0 + p.tap_shift[tap]);
+          tma_load_2d_2sm(sa + A_BYTES, &tmB, fb, kc * BLOCK_K, b_row0);
+          if (++stage == TWO_SM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA only): M = 256 over the pair, N = 256 =====
+    int stage = 0;
+    uint32_t phase = 0;
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    int it = 0;
+    for (int t = cluster_id; t < total; t += n_clusters, ++it) {
+      const int acc = it & 1;
+      mbar_wait(tempty_bar0 + 8 * acc, ((it >> 1) & 1) ^ 1);       // both CTAs' epilogues have drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * BN;
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(full_bar0 + 8 * stage, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16_2sm(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(empty_bar0 + 8 * stage);
+          if (kc == p.k_chunks - 1) umma_commit_2sm(tfull_bar0 + 8 * acc);
+        }
+        __syncwarp();
+        if (++stage == TWO_SM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps (both CTAs): this CTA's 128 rows x 256 columns =====
+    const int ew = warp - 4;
+    const int q = warp & 3, half = ew >> 2;
+    float* stage_buf = reinterpret_cast<float*>(smem_raw + (staging - raw)) + ew * (32 * (64 + 4));
+    int it = 0;
+    for (int t = cluster_id; t < total; t += n_clusters, ++it) {
+      const int g = t / tiles_per_group, r = t - g * tiles_per_group;
+      const int n_tile = r % tiles_n;
+      const int m0 = (r / tiles_n) * 256 + (int)rank * 128, n0 = n_tile * BN;
+      const int acc = it & 1;
+      mbar_wait(tfull_bar0 + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tb = tempty_bar0 + 8 * acc;
+      tile_epilogue<BN, EPI>(p, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tb, 0);                   // the leader's barrier (also from the leader itself)
+      });
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                               // nobody leaves while the pair still signals / reads
+  tc_fence_after();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace mk

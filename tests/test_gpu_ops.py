@@ -204,6 +204,25 @@ def test_attention(T, heads, scale, impl):
     assert rel_err(out, ref) < 2e-3
 
 
+@pytest.mark.skipif(os.environ.get("MICKEY_TEST_EXPERIMENTAL") != "1" or os.environ.get("MICKEY_GEMM_2SM") != "1",
+                    reason="cta_group::2 GEMM: written after the round-1 GPU budget was spent, not yet run on hardware "
+                           "(run with MICKEY_TEST_EXPERIMENTAL=1 MICKEY_GEMM_2SM=1)")
+def test_gemm_2sm_experimental():
+    """With MICKEY_GEMM_2SM=1 every persistent-route GEMM with N % 256 == 0 runs on gemm_tc_2sm_kernel (256 x 256 tiles
+    over a CTA pair)."""
+    for M, N, K in ((20000, 1536, 768), (4100, 512, 1024), (256, 256, 768)):
+        a, w, bias = _rand(M, K, seed=70).half(), _rand(N, K, scale=0.05, seed=71).half(), _rand(N, scale=0.1, seed=72)
+        out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+        gemm("STORE_H", a, w, M, N, K, bias=bias, act=1, out_h=out, out_h_ld=N)
+        assert rel_err(out, F.gelu(a.float() @ w.float().t() + bias)) < 2e-3, (M, N, K)
+    M, N, K = 30000, 768, 768
+    a, w = _rand(M, K, seed=73).half(), _rand(N, K, scale=0.05, seed=74).half()
+    bias, gamma, x = _rand(N, scale=0.1, seed=75), _rand(N, seed=76), _rand(M, N, seed=77)
+    ref = x + gamma * (a.float() @ w.float().t() + bias)
+    gemm("RESID_F", a, w, M, N, K, bias=bias, gamma=gamma, out_f=x, out_f_ld=N)
+    assert rel_err(x, ref) < 1e-5
+
+
 @pytest.mark.skipif(os.environ.get("MICKEY_TEST_EXPERIMENTAL") != "1",
                     reason="ping-pong attention kernel: written after the round-1 GPU budget was spent, not yet run on hardware")
 @pytest.mark.parametrize("T,heads,scale", [(211, 6, 1.5), (1939, 6, 1.5), (64, 12, 1.5), (300, 6, 6.0), (513, 6, 1.5)])
