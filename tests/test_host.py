@@ -97,3 +97,30 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in lib.mk_version()
     assert ctypes.sizeof(_lib.MkConfig) == lib.mk_sizeof_config()
     assert ctypes.sizeof(_lib.MkGemmArgs) == lib.mk_sizeof_gemm_args()
+
+
+def test_hot_kernels_are_tcgen05_tma_tmem_in_sass():
+    """Static evidence that the hot path is what DESIGN.md says it is: the GEMM family and the attention kernel of the
+    built library issue UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor loads) and LDTM (tcgen05.ld from TMEM); the SASS
+    mnemonics are the ones B200_PROFILING.md lists.  Needs cuobjdump (part of the CUDA toolkit of this image)."""
+    import shutil
+    import subprocess
+    from mickey_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    so = _lib.library_path() if hasattr(_lib, "library_path") else os.path.join(os.path.dirname(_lib.__file__), "_C", "libmickey_b200.so")
+    sass = subprocess.run([exe, "-sass", so], capture_output=True, text=True, timeout=300).stdout
+    per, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            per[cur] = {"UTCHMMA": 0, "UTMALDG": 0, "LDTM": 0}
+        elif cur:
+            for k in per[cur]:
+                if k in line:
+                    per[cur][k] += 1
+    hot = {n: c for n, c in per.items() if any(t in n for t in ("gemm_tc_kernel", "gemm_tc_persistent_kernel", "attention_tc_kernel"))}
+    assert len(hot) >= 30
+    for name, c in hot.items():
+        assert c["UTCHMMA"] > 0 and c["UTMALDG"] > 0 and c["LDTM"] > 0, (name, c)
