@@ -128,7 +128,7 @@ def basic_block(sd, pre: str, x: Tensor, relu: bool = True, bn: bool = True) -> 
 # ------------------------------------------------------------------------------------------------
 # a10: linear-attention transformer inside each head
 # ------------------------------------------------------------------------------------------------
-def sine_position_encoding(d_model: int, h: int, w: int, dtype=torch.float32) -> Tensor:
+def sine_position_encoding(d_model: int, h: int, w: int, dtype=torch.float32, device=None) -> Tensor:
     """modules/att_layers/transformer.py:25-36: [d_model, h, w]; positions start at 1."""
     y = torch.arange(1, h + 1, dtype=torch.float32).view(1, h, 1).expand(1, h, w)
     x = torch.arange(1, w + 1, dtype=torch.float32).view(1, 1, w).expand(1, h, w)
@@ -139,7 +139,7 @@ def sine_position_encoding(d_model: int, h: int, w: int, dtype=torch.float32) ->
     pe[1::4] = torch.cos(x * div)
     pe[2::4] = torch.sin(y * div)
     pe[3::4] = torch.cos(y * div)
-    return pe.to(dtype)
+    return pe.to(dtype).to(device) if device is not None else pe.to(dtype)
 
 
 def linear_attention(q: Tensor, k: Tensor, v: Tensor, eps: float = 1e-6) -> Tensor:
@@ -172,7 +172,7 @@ def head_transformer(sd, pre: str, x: Tensor, add_pos_enc: bool) -> Tensor:
     """modules/att_layers/transformer.py:75-103 (3 'self' layers, linear attention, 8 heads)."""
     B, C, H, W = x.shape
     if add_pos_enc:
-        x = x + sine_position_encoding(C, H, W, x.dtype)[None]
+        x = x + sine_position_encoding(C, H, W, x.dtype, x.device)[None]
     t = x.flatten(2).transpose(1, 2)
     n_layers = 1 + max(int(k[len(pre + "layers."):].split(".")[0]) for k in sd if k.startswith(pre + "layers."))
     for i in range(n_layers):
@@ -219,7 +219,10 @@ def extractor(sd, img: Tensor, cfg) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     f = m["DINOV2"]["DOWN_FACTOR"]
     B, _, H, W = img.shape
     img = img[:, :, : f * (H // f), : f * (W // f)]
-    tok = vit_forward_features(sd, img)
+    # FLOAT16: True (mickey_extractor.py:31-35,49) == backbone weights stored in fp16: the image is cast to the
+    # backbone's dtype and the patch tokens come back as fp32 (used by bench.py's eager-CUDA comparator)
+    wdt = sd[BACKBONE + "patch_embed.proj.weight"].dtype
+    tok = vit_forward_features(sd, img.to(wdt)).float()
     feat = tok.permute(0, 2, 1).reshape(B, -1, H // f, W // f)
     kp, ds = m["KP_HEADS"], m["DSC_HEAD"]
     bn = kp["BN"]
@@ -258,8 +261,8 @@ def dual_softmax(dsc0: Tensor, dsc1: Tensor, temperature: float, dustbin: Option
 def absolute_keypoints(offsets: Tensor, down_factor: int) -> Tensor:
     """modules/compute_correspondences.py:20-31: (offset + (x, y) cell index) * 14."""
     B, _, H, W = offsets.shape
-    xs = torch.arange(W, dtype=offsets.dtype).view(1, 1, 1, W).expand(B, 1, H, W)
-    ys = torch.arange(H, dtype=offsets.dtype).view(1, 1, H, 1).expand(B, 1, H, W)
+    xs = torch.arange(W, dtype=offsets.dtype, device=offsets.device).view(1, 1, 1, W).expand(B, 1, H, W)
+    ys = torch.arange(H, dtype=offsets.dtype, device=offsets.device).view(1, 1, H, 1).expand(B, 1, H, W)
     return (offsets + torch.cat([xs, ys], dim=1)) * down_factor
 
 
@@ -307,7 +310,7 @@ def kabsch(A: Tensor, Bp: Tensor, w: Optional[Tensor] = None) -> Tuple[Tensor, T
         b_mean = (wn * Bp).sum(1, keepdim=True)
         H = (A - a_mean).transpose(1, 2) @ (w.unsqueeze(-1) * (Bp - b_mean))
     U, _, V = torch.svd(H)
-    Z = torch.eye(3, dtype=A.dtype).repeat(A.shape[0], 1, 1)
+    Z = torch.eye(3, dtype=A.dtype, device=A.device).repeat(A.shape[0], 1, 1)
     Z[:, 2, 2] = torch.sign(torch.linalg.det(U @ V.transpose(1, 2)))
     R = V @ Z @ U.transpose(1, 2)
     t = b_mean - a_mean @ R.transpose(1, 2)
@@ -345,13 +348,14 @@ def solve_pose(final_scores: Tensor, kps0: Tensor, depth0: Tensor, kps1: Tensor,
     p = cfg["PROCRUSTES"]
     IM, IR, n_s, n_c = p["IT_MATCHES"], p["IT_RANSAC"], p["NUM_SAMPLED_MATCHES"], p["NUM_CORR_3D_3D"]
     B, N, _ = final_scores.shape
+    dev = final_scores.device
     K0, K1 = K0.to(final_scores.dtype), K1.to(final_scores.dtype)
     rows = final_scores.reshape(B, N * N)
     try:
         if outer_idx is None:
             tiled = rows.unsqueeze(1).expand(B, IM, N * N).reshape(B * IM, N * N)
             outer_idx = torch.multinomial(tiled, n_s, generator=generator)              # :231
-        b_of = torch.arange(B).repeat_interleave(IM)                                     # [B*IM]
+        b_of = torch.arange(B, device=dev).repeat_interleave(IM)                                     # [B*IM]
         i0 = torch.div(outer_idx, N, rounding_mode="trunc")                              # :233
         i1 = outer_idx % N                                                               # :234
         bb = b_of[:, None].expand(-1, n_s)
@@ -365,7 +369,7 @@ def solve_pose(final_scores: Tensor, kps0: Tensor, depth0: Tensor, kps1: Tensor,
         if inner_idx is None:
             wv = wts.unsqueeze(1).expand(B * IM, IR, n_s).reshape(B * IM * IR, n_s)
             inner_idx = torch.multinomial(wv, n_c, generator=generator)                  # :251
-        s_of = torch.arange(B * IM).repeat_interleave(IR)                                # hypothesis -> set
+        s_of = torch.arange(B * IM, device=dev).repeat_interleave(IR)                                # hypothesis -> set
         Xk = X[s_of[:, None], inner_idx]                                                 # [M,3,3]
         Yk = Y[s_of[:, None], inner_idx]
         R, t = kabsch(Xk, Yk)                                                            # :259
@@ -373,13 +377,13 @@ def solve_pose(final_scores: Tensor, kps0: Tensor, depth0: Tensor, kps1: Tensor,
                        torch.isnan(R).any() or torch.isinf(R).any())                     # :261-262
         score = soft_inliers(X[s_of], Y[s_of], R, t, p["TH_SOFT_INLIER"]).reshape(B, IM * IR)   # :265
         best = torch.argmax(score, dim=1)                                                # :275
-        bi = torch.arange(B)
+        bi = torch.arange(B, device=dev)
         R = R.reshape(B, IM * IR, 3, 3)[bi, best]
         t = t.reshape(B, IM * IR, 1, 3)[bi, best]
         best_set = bi * IM + torch.div(best, IR, rounding_mode="trunc")
         Xb, Yb = X[best_set], Y[best_set]
-        mask_ref = torch.zeros(B, n_s, dtype=X.dtype)
-        prev = n_c * torch.ones(B, dtype=X.dtype)                                        # :285
+        mask_ref = torch.zeros(B, n_s, dtype=X.dtype, device=dev)
+        prev = n_c * torch.ones(B, dtype=X.dtype, device=dev)                                        # :285
         n_ref_done = 0
         for _ in range(p["NUM_REFINEMENTS"]):                                            # :286-300
             inl = hard_inliers(Xb, Yb, R, t, p["TH_INLIER"])
@@ -412,7 +416,7 @@ def solve_pose(final_scores: Tensor, kps0: Tensor, depth0: Tensor, kps1: Tensor,
         if invalid:
             raise FloatingPointError("invalid hypothesis")
     except Exception:                                                                    # :331-342
-        R = torch.zeros(B, 3, 3); t = torch.zeros(B, 1, 3); inliers = torch.zeros(B)
+        R = torch.zeros(B, 3, 3, device=dev); t = torch.zeros(B, 1, 3, device=dev); inliers = torch.zeros(B, device=dev)
         inl_list = [torch.zeros(0, 5)] * B
     if return_inliers:
         return R, t, inliers, inl_list

@@ -22,6 +22,13 @@ GOLDEN_CASES = {
     # BASELINE config 2 at full size (N=1938): N x N tensors stored with stride 17
     "vits_720x540": dict(variant="vits", it_matches=8, it_ransac=64, batch=1, height=720, width=540,
                          weight_seed=0, data_seed=7, rng_seed=11, stride=17),
+    # BASELINE config 3's model at full size: ViT-B/14, 1024 hypotheses (16x64), two pairs (T = 1939 attention tails,
+    # 128x256 persistent GEMM tiles, batched matcher) — N x N tensors strided by 17
+    "vitb_720x540": dict(variant="vitb", it_matches=16, it_ransac=64, batch=2, height=720, width=540,
+                         weight_seed=3, data_seed=9, rng_seed=12, stride=17),
+    # the reference's default model at full size: ViT-L/14, 2000 hypotheses (20x100)
+    "vitl_720x540": dict(variant="vitl", it_matches=20, it_ransac=100, batch=1, height=720, width=540,
+                         weight_seed=4, data_seed=10, rng_seed=13, stride=17),
 }
 
 

@@ -38,14 +38,27 @@ def run_case(name, spec):
         draws.append(out.clone())
         return out
 
+    # the hypothesis scores and the winner (probabilisticProcrustes.py:265,275) are internal to the solver: record the
+    # argument and the result of its single torch.argmax(score_k, dim=1) call
+    picks = []
+    orig_argmax = torch.argmax
+
+    def recording_argmax(inp, *a, **k):
+        out = orig_argmax(inp, *a, **k)
+        if inp.dim() == 2 and (k.get("dim") == 1 or (a and a[0] == 1)):
+            picks.append((inp.clone(), out.clone()))
+        return out
+
     torch.manual_seed(spec["rng_seed"])
     torch.multinomial = recording_multinomial
+    torch.argmax = recording_argmax
     try:
         with torch.no_grad():
             R, t = model(data, return_inliers=True)
     finally:
         torch.multinomial = orig
-    assert len(draws) == 2
+        torch.argmax = orig_argmax
+    assert len(draws) == 2 and len(picks) == 1
     st = spec.get("stride", 1)
     out = {
         "kps0": data["kps0"], "kps1": data["kps1"],
@@ -56,6 +69,7 @@ def run_case(name, spec):
         "final_scores": data["final_scores"][:, ::st, ::st],
         "scores_rowsum": data["scores"].sum(-1), "final_rowsum": data["final_scores"].double().sum(-1),
         "outer_idx": draws[0].to(torch.int32), "inner_idx": draws[1].to(torch.int16),
+        "hyp_scores": picks[0][0], "best": picks[0][1].to(torch.int32),
         "R": R, "t": t, "inliers": data["inliers"],
         "n_inliers_list": torch.tensor([len(x) for x in data["inliers_list"]]),
         "inliers_list0": data["inliers_list"][0],

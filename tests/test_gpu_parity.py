@@ -51,7 +51,10 @@ def _to_dev(d):
     return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in d.items()}
 
 
-@pytest.mark.parametrize("name", ["vits_small", "vitb_small", "vitl_small", "vits_720x540"])
+ALL_GOLDEN = ["vits_small", "vitb_small", "vitl_small", "vits_720x540", "vitb_720x540", "vitl_720x540"]
+
+
+@pytest.mark.parametrize("name", ALL_GOLDEN)
 def test_extract_and_match_vs_reference_golden(name):
     spec, gold = GOLDEN_CASES[name], load_golden(name)
     cfg, model = _model(spec["variant"], spec["it_matches"], spec["it_ransac"], spec["weight_seed"])
@@ -69,11 +72,12 @@ def test_extract_and_match_vs_reference_golden(name):
     e["final_scores"] = rel_err(data["_final_scores_fused"][:, ::st, ::st], gold["final_scores"])
     e["scores_rowsum"] = rel_err(data["scores"].sum(-1), gold["scores_rowsum"])
     _record(name, **e)
-    assert e["dsc"] < 1e-3, e                  # north_star: 1e-3 relative on descriptors
-    assert e["kps_px"] < 2e-2, e
-    assert e["depth"] < 2e-3 and e["scr"] < 2e-3, e
-    assert e["kp_scores"] < 4e-3, e
-    assert e["scores"] < 1e-2 and e["final_scores"] < 1e-2 and e["scores_rowsum"] < 3e-3, e
+    # north_star: 1e-3 relative on descriptors and scores (measured: profiles/r02_parity.json)
+    assert e["dsc"] < 1e-3, e
+    assert e["scores"] < 1e-3 and e["final_scores"] < 1e-3 and e["scores_rowsum"] < 1e-3, e
+    assert e["kp_scores"] < 1e-4 and e["scr"] < 1e-4, e
+    assert e["kps_px"] < 3e-2, e
+    assert e["depth"] < 2e-3, e
 
 
 def test_matcher_alone_vs_oracle_fp32_inputs():
@@ -149,6 +153,132 @@ def test_solver_with_injected_reference_draws(name):
         assert e["rot_deg"] < 1e-2 and e["t_m"] < 1e-3 and e["inliers"] < 1e-3, e
         assert [len(x) for x in lst] == gold["n_inliers_list"].tolist()
         assert rel_err(lst[0], gold["inliers_list0"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["vits_small", "vits_720x540", "vitb_720x540", "vitl_720x540"])
+def test_pose_from_cuda_features_with_reference_draws(name):
+    """north_star end to end: CUDA features (fp16 tensor-core backbone + heads, CUDA matcher) and the reference's own
+    two multinomial draws through the CUDA solver -> R, t against the reference's pose (1e-2 deg / 1e-3 m).  The
+    hypothesis scores and the winner of the reference are part of the fixture (recorded around its torch.argmax);
+    a different winner is accepted only between hypotheses whose reference scores tie within 1e-3."""
+    spec, gold = GOLDEN_CASES[name], load_golden(name)
+    cfg, model = _model(spec["variant"], spec["it_matches"], spec["it_ransac"], spec["weight_seed"])
+    data = _to_dev(synthetic_pair(spec["batch"], spec["height"], spec["width"], seed=spec["data_seed"]))
+    model.compute_matches(data)
+    data["final_scores"] = data.pop("_final_scores_fused")
+    R, t, inl, lst = model.e2e_Procrustes.estimate_pose_vectorized(
+        data, return_inliers=True, outer_idx=gold["outer_idx"], inner_idx=gold["inner_idx"].int())
+    res = data["_solver"]
+    torch.cuda.synchronize()
+    assert int(res["status"].item()) == 0
+    hyp, ghyp = res["hyp_scores"].cpu().double(), gold["hyp_scores"].double()
+    close = (hyp - ghyp).abs() <= 1e-3 * ghyp.abs().clamp_min(1.0)
+    win = hyp.argmax(1)
+    same = bool((win == gold["best"].long()).all())
+    e = dict(hyp_frac_within_1e3=float(close.double().mean()), same_winner=float(same),
+             rot_deg=float(rotation_angle_deg(R, gold["R"]).max()), t_m=float((t.cpu() - gold["t"]).abs().max()),
+             inliers=rel_err(inl.reshape(-1), gold["inliers"].reshape(-1)))
+    _record("pose_e2e_" + name, **e)
+    # ill-conditioned 3-point samples (rank-1 covariance) have no unique Kabsch optimum (see the test above): they are
+    # a few percent of the hypotheses and never win
+    assert e["hyp_frac_within_1e3"] > 0.9, e
+    tied = ghyp.gather(1, win[:, None])[:, 0] >= ghyp.max(1).values * (1 - 1e-3)
+    assert bool(tied.all()), e
+    if same:
+        assert e["rot_deg"] < 1e-2 and e["t_m"] < 1e-3, e
+        assert e["inliers"] < 1e-2, e
+        assert [len(x) for x in lst] == gold["n_inliers_list"].tolist()
+
+
+def test_failure_contract_zero_pose():
+    """probabilisticProcrustes.py:228,331-342: any failure inside the vectorised solver (multinomial cannot draw 2048
+    non-zero cells; a non-finite hypothesis) gives R = 0, t = 0, inliers = 0 and empty inlier lists for the WHOLE batch,
+    and the call itself succeeds."""
+    cfg, model = _model("vits", 4, 16, 0)
+    gh, gw, B = 15, 14, 2
+    N = gh * gw
+    eng = model._engine()
+    eng._ws_for(B, 14 * gh, 14 * gw)
+    g = torch.Generator().manual_seed(0)
+    kps = torch.rand(B, 2, N, generator=g) * 200
+    depth = torch.rand(B, 1, N, generator=g) + 1
+    K = torch.tensor([[[549.7, 0, 268.7], [0, 549.7, 351.8], [0, 0, 1.0]]]).repeat(B, 1, 1)
+    # (1) fewer than NUM_SAMPLED_MATCHES non-zero cells in one pair of the batch
+    fs = torch.rand(B, N, N, generator=g) * 1e-6
+    fs[1].zero_()
+    fs[1].view(-1)[:100] = 1e-6
+    b = _to_dev(dict(final_scores=fs, kps0=kps, kps1=kps.flip(-1), depth_kp0=depth, depth_kp1=depth, K_color0=K, K_color1=K))
+    R, t, inl, lst = model.e2e_Procrustes.estimate_pose_vectorized(b, return_inliers=True, seed=3)
+    torch.cuda.synchronize()
+    assert int(b["_solver"]["status"].item()) & 1
+    assert float(R.abs().max()) == 0 and float(t.abs().max()) == 0 and float(inl.abs().max()) == 0
+    assert len(lst) == B and all(x.shape[0] == 0 for x in lst)
+    # (2) a NaN depth reaches a hypothesis -> non-finite pose -> zero pose (:261-262, 329)
+    fs = torch.rand(B, N, N, generator=g) * 1e-6
+    dn = depth.clone()
+    dn[0, 0, :] = float("nan")
+    b = _to_dev(dict(final_scores=fs, kps0=kps, kps1=kps.flip(-1), depth_kp0=dn, depth_kp1=depth, K_color0=K, K_color1=K))
+    R, t, inl = model.e2e_Procrustes.estimate_pose_vectorized(b, seed=3)
+    torch.cuda.synchronize()
+    assert int(b["_solver"]["status"].item()) & 4
+    assert float(R.abs().max()) == 0 and float(t.abs().max()) == 0 and float(inl.abs().max()) == 0
+    # (3) the same contract through model(data): on a 7x7 token grid the 3-cell border mask (mickey_extractor.py:112-118)
+    # leaves one non-zero score per image, so final_scores has ONE non-zero cell and the reference's multinomial raises
+    data = _to_dev(synthetic_pair(1, 98, 98, seed=1))
+    R, t = model(data, return_inliers=True)
+    torch.cuda.synchronize()
+    assert int((data["final_scores"] > 0).sum()) == 1
+    assert float(R.abs().max()) == 0 and float(t.abs().max()) == 0 and float(data["inliers"].abs().max()) == 0
+    assert len(data["inliers_list"]) == 1 and data["inliers_list"][0].shape[0] == 0
+    # the oracle (reference restatement) agrees on (1)
+    Ro, to, io = mo.solve_pose(fs.zero_(), kps, depth, kps.flip(-1), depth, K, K, cfg)
+    assert float(Ro.abs().max()) == 0 and float(io.abs().max()) == 0
+
+
+_FLAG_CASES = {
+    "no_score_softmax": {"MICKEY.KP_HEADS.USE_SOFTMAX": False},
+    "depth_sigmoid": {"MICKEY.KP_HEADS.USE_DEPTHSIGMOID": True},
+    "no_dustbin": {"FEATURE_MATCHER.DUAL_SOFTMAX.USE_DUSTBIN": False},
+    "no_pos_encoding": {"MICKEY.KP_HEADS.POS_ENCODING": False, "MICKEY.DSC_HEAD.POS_ENCODING": False},
+    "raw_descriptors": {"MICKEY.DSC_HEAD.NORM_DSC": False, "FEATURE_MATCHER.DUAL_SOFTMAX.TEMPERATURE": 20.0},
+}
+
+
+def _cfg_with(variant, im, ir, overrides, float16=True):
+    cfg = mickey_cfg(variant, im, ir, float16=float16)
+    for dotted, v in overrides.items():
+        node = cfg
+        parts = dotted.split(".")
+        for p in parts[:-1]:
+            node = node[p]
+        node[parts[-1]] = v
+    return cfg
+
+
+@pytest.mark.parametrize("case", sorted(_FLAG_CASES))
+def test_non_default_config_branches_vs_oracle(case):
+    """The config branches the released YAML does not take (mickey_extractor.py:112-124,213-216,248-249;
+    feature_matcher.py:66-81; transformer.py:88-92), CUDA path vs the CPU oracle on a 15x14 grid."""
+    ov = _FLAG_CASES[case]
+    cfg = _cfg_with("vits", 2, 8, ov)
+    model = MickeyRelativePose(cfg)
+    sd = synthetic_state_dict(cfg, seed=6)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    pair = synthetic_pair(2, 210, 196, seed=12)
+    data = _to_dev(dict(pair))
+    model.compute_matches(data)
+    torch.cuda.synchronize()
+    cfg32 = _cfg_with("vits", 2, 8, ov, float16=False)
+    with torch.no_grad():
+        ref = mo.compute_correspondences(sd, dict(pair), cfg32)
+    e = {k: rel_err(data[k], ref[k]) for k in ("kps0", "depth_kp0", "depth_kp1", "scr0", "scr1", "dsc0", "dsc1", "scores", "kp_scores")}
+    e["final_scores"] = rel_err(data["_final_scores_fused"], ref["final_scores"])
+    _record("flags_" + case, **e)
+    assert bool(torch.isfinite(data["scores"]).all())
+    assert e["dsc0"] < 1e-3 and e["dsc1"] < 1e-3, e
+    assert e["scores"] < 2e-3 and e["final_scores"] < 2e-3, e          # un-normalised descriptors: logits up to +-30
+    assert e["scr0"] < 1e-3 and e["kp_scores"] < 1e-3 and e["depth_kp0"] < 2e-3 and e["kps0"] < 1e-3, e
 
 
 @pytest.mark.parametrize("grid,batch", [((20, 16), 2), ((51, 38), 1)])

@@ -29,7 +29,7 @@ def _run_oracle(name, inject=True):
     return spec, gold, data, trace
 
 
-@pytest.mark.parametrize("name", ["vits_small", "vitb_small", "vitl_small", "vits_720x540"])
+@pytest.mark.parametrize("name", ["vits_small", "vitb_small", "vitl_small", "vits_720x540", "vitb_720x540", "vitl_720x540"])
 def test_oracle_matches_reference_golden(name):
     spec, gold, data, _ = _run_oracle(name)
     st = spec["stride"]
