@@ -68,6 +68,13 @@ long long mk_workspace_offset(mk_handle* h, const char* name, int n_pairs, int i
 int mk_extract(mk_handle* h, const float* images_dev, int n_pairs, int img_h, int img_w, float* kps_dev,
                float* depth_dev, float* scr_dev, float* dsc_dev, void* ws_dev, long long ws_bytes, void* stream);
 
+/* Same stage fed by uint8 images straight from the decoder: images_u8_dev uint8 [2*n_pairs, H, W, 3],
+ * RGB, HWC — what lib/datasets/utils.py:61-71 (cv2.imread -> cvtColor -> resize) holds before `.float() / 255`
+ * (:74); the division, the crop to multiples of 14 (mickey_extractor.py:46) and the patch gather happen in one kernel,
+ * bit-identical to mk_extract on the reference's float tensor. */
+int mk_extract_u8(mk_handle* h, const unsigned char* images_u8_dev, int n_pairs, int img_h, int img_w, float* kps_dev,
+                  float* depth_dev, float* scr_dev, float* dsc_dev, void* ws_dev, long long ws_bytes, void* stream);
+
 /* ---- stage 2: dual-softmax matcher
  * replaces featureMatcher/dualSoftmax.forward (feature_matcher.py:48-83), kp_matrix_scores
  * (compute_correspondences.py:46-50) and `final_scores = scores * kp_scores` (compute_pose.py:23).
@@ -101,6 +108,19 @@ int mk_forward(mk_handle* h, const float* images_dev, const float* K0_dev, const
                float* dsc_dev, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, float* pose_dev,
                int* best_set_dev, float* inlier_mask_dev, int* sampled_idx_out_dev, int* status_dev, void* ws_dev,
                long long ws_bytes, void* stream);
+
+int mk_forward_u8(mk_handle* h, const unsigned char* images_u8_dev, const float* K0_dev, const float* K1_dev, int n_pairs,
+                  int img_h, int img_w, unsigned long long seed, float* kps_dev, float* depth_dev, float* scr_dev,
+                  float* dsc_dev, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, float* pose_dev,
+                  int* best_set_dev, float* inlier_mask_dev, int* sampled_idx_out_dev, int* status_dev, void* ws_dev,
+                  long long ws_bytes, void* stream);
+
+/* ---- after the path: submission records (replaces the per-pair loop of submission.py:43-59)
+ * pose_dev fp32 [n_pairs,13] as written by mk_forward / mk_solve_pose -> out_dev fp64 [n_pairs, 9] =
+ * qw qx qy qz | tx ty tz | inliers | valid.  Quaternion = transforms3d.quaternions.mat2quat(R) (principal eigenvector
+ * of the symmetric 4x4 K(R), w >= 0) computed in fp64; valid = 0 where the reference skips the frame
+ * (np.isnan(R).any() or np.isnan(t).any() or np.isinf(t).any(), submission.py:51-52).  One D2H copy per batch. */
+int mk_pose_to_submission(const float* pose_dev, int n_pairs, double* out_dev, void* stream);
 
 /* (Re)seed the solver's device-side generator on `stream` (used in front of a CUDA-graph replay of mk_forward
  * captured with seed = 0). */
@@ -141,6 +161,8 @@ typedef struct mk_gemm_args {
 int mk_op_gemm(const mk_gemm_args* args, void* stream);
 int mk_op_patch_gather(const float* img, void* patches_h, int n_img, int H, int W, int kpad, float* x_f,
                        const float* cls_pos, int D, void* stream);
+int mk_op_ingest_u8(const unsigned char* img_u8, void* patches_h, int n_img, int H, int W, int kpad, float* x_f,
+                    const float* cls_pos, int D, void* stream);
 int mk_op_layernorm(const float* x, const float* w, const float* b, void* out_h, int rows, int D, float eps, int mode,
                     int gh, int gw, void* stream);
 /* impl: 0 = default (tcgen05), 1 = tcgen05/TMEM kernel, 2 = mma.sync kernel (cross-check),

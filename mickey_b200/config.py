@@ -12,8 +12,20 @@ derived from CHANNEL_DIM (384 / 768 / 1024).
 """
 from __future__ import annotations
 
+import ast
 import copy
 import yaml
+
+
+def _decode(v):
+    """yacs semantics (yacs/config.py `_decode_cfg_value`): a string that parses as a Python literal becomes that
+    literal ('None' -> None, '[1, 2]' -> [1, 2]); anything else stays a string."""
+    if not isinstance(v, str):
+        return v
+    try:
+        return ast.literal_eval(v)
+    except (ValueError, SyntaxError):
+        return v
 
 
 class CfgNode(dict):
@@ -44,7 +56,7 @@ class CfgNode(dict):
             if isinstance(v, dict) and isinstance(self[k], CfgNode):
                 self[k].merge_from_other_cfg(v, _path + k + ".")
             else:
-                self[k] = CfgNode(v) if isinstance(v, dict) else v
+                self[k] = CfgNode(v) if isinstance(v, dict) else _decode(v)
 
     def merge_from_file(self, path):
         with open(path, "r") as f:
@@ -60,7 +72,7 @@ class CfgNode(dict):
                 node = node[p]
             if parts[-1] not in node:
                 raise KeyError(f"Non-existent config key: {key}")
-            node[parts[-1]] = val
+            node[parts[-1]] = _decode(val)
 
     def dump(self):
         def plain(n):

@@ -300,16 +300,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
 
 int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s) {
   if (D != heads * FA_D) { set_last_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads); return MK_ERR_UNSUPPORTED; }
-  static bool attr = false;
+  static unsigned long long attr_mask = 0;
   static int poly = 0;
-  if (!attr) {
+  if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     // default: every 4th pair (25 %) on the FMA pipe -- measured 32.0 -> 29.9 us (one 720x540 pair) and 1156 -> 1100 us
     // (64 images, ViT-B); 12.5 % gives half of that, 50 % is slower than none (issue-bound).  MICKEY_ATTN_POLY=0 disables.
     const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : 4;
-    attr = true;
   }
   CUtensorMap tm;
   int rc = make_tensor_map_f16(&tm, qkv, (long long)n_img * T, 3LL * D, 3LL * D, FA_BQ);
@@ -565,10 +564,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
 
 int attention_pp(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s) {
   if (D != heads * FA_D) { set_last_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads); return MK_ERR_UNSUPPORTED; }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));
-    attr = true;
   }
   CUtensorMap tm;
   int rc = make_tensor_map_f16(&tm, qkv, (long long)n_img * T, 3LL * D, 3LL * D, FA_BQ);

@@ -68,6 +68,17 @@ struct GemmParams {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Function attributes (cudaFuncSetAttribute) and the SM count belong to a DEVICE: one-time setup is keyed on the
+// current device, not on the process (a second handle on cuda:1 must run its own).
+static inline bool first_use_on_device(unsigned long long& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // Every kernel of the pipeline is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it lets the
 // NEXT kernel's CTAs be scheduled as soon as this grid has issued pdl_trigger() and SM resources free up, so the

@@ -175,14 +175,18 @@ int gemm(mk_handle* h, const char* tag, int epi, const void* a, long long a_rows
 #define MK_KERNEL(tag, call) do { ProfScope ps_(h, tag, st); h->launches++; MK_TRY(call); } while (0)
 
 // ---- stage 1 ----------------------------------------------------------------------------------------------
-int run_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, float* kps, float* depth, float* scr,
+// img_fmt 0: fp32 NCHW in [0,1] (the reference's tensors); 1: uint8 NHWC RGB as cv2 delivers it (mk_*_u8)
+int run_extract(mk_handle* h, const void* images, int img_fmt, int n_pairs, int H, int W, float* kps, float* depth, float* scr,
                 float* dsc, Workspace& w, cudaStream_t st) {
   const mk_config& c = h->cfg;
   const Geo g = make_geo(n_pairs, H, W);
   const int D = c.embed_dim;
   Lookup L{h};
   // -- tokens: patch embedding + cls + position embedding (dinov2.py:191-200)
-  MK_KERNEL("vit.patch_gather", patch_gather(images, w.P, g.n_img, H, W, KPAD, w.X, L.f("patch.clspos", D), D, st));
+  if (img_fmt == 1)
+    MK_KERNEL("vit.ingest_u8", ingest_u8(reinterpret_cast<const uint8_t*>(images), w.P, g.n_img, H, W, KPAD, w.X, L.f("patch.clspos", D), D, st));
+  else
+    MK_KERNEL("vit.patch_gather", patch_gather(reinterpret_cast<const float*>(images), w.P, g.n_img, H, W, KPAD, w.X, L.f("patch.clspos", D), D, st));
   {
     GemmParams p = base_params(g.Mp, D, KPAD);
     p.aux = L.f("patch.posb", (long long)g.N * D); p.tok_per_img = g.N; p.out_f = w.X; p.out_f_ld = D;
@@ -405,6 +409,7 @@ int run_solve(mk_handle* h, const float* final_scores, const float* kps, const f
 
 int check_ws(mk_handle* h, int n_pairs, int H, int W, void* ws, long long ws_bytes, Workspace& out) {
   if (!h || !h->finalized) { set_last_error("handle not finalized"); return MK_ERR_INVALID; }
+  MK_CUDA_CHECK(cudaSetDevice(h->device));        // one handle per device: every entry point runs on the handle's device
   if (H != h->geo_h || W != h->geo_w) {
     set_last_error("geometry %dx%d does not match the finalized geometry %dx%d", H, W, h->geo_h, h->geo_w);
     return MK_ERR_INVALID;
@@ -488,7 +493,14 @@ int mk_extract(mk_handle* h, const float* images, int n_pairs, int H, int W, flo
                float* dsc, void* ws, long long ws_bytes, void* stream) {
   Workspace w;
   MK_TRY(check_ws(h, n_pairs, H, W, ws, ws_bytes, w));
-  return run_extract(h, images, n_pairs, H, W, kps, depth, scr, dsc, w, (cudaStream_t)stream);
+  return run_extract(h, images, 0, n_pairs, H, W, kps, depth, scr, dsc, w, (cudaStream_t)stream);
+}
+
+int mk_extract_u8(mk_handle* h, const unsigned char* images, int n_pairs, int H, int W, float* kps, float* depth, float* scr,
+                  float* dsc, void* ws, long long ws_bytes, void* stream) {
+  Workspace w;
+  MK_TRY(check_ws(h, n_pairs, H, W, ws, ws_bytes, w));
+  return run_extract(h, images, 1, n_pairs, H, W, kps, depth, scr, dsc, w, (cudaStream_t)stream);
 }
 
 int mk_match(mk_handle* h, int n_pairs, float* scores, float* kp_scores, float* final_scores, void* ws,
@@ -511,18 +523,39 @@ int mk_solve_pose(mk_handle* h, const float* final_scores, const float* kps, con
                    inl_mask, sampled_out, hyp_scores_out, status, w, (cudaStream_t)stream);
 }
 
-int mk_forward(mk_handle* h, const float* images, const float* K0, const float* K1, int n_pairs, int H, int W,
-               unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
-               float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
-               int* status, void* ws, long long ws_bytes, void* stream) {
+static int forward_any(mk_handle* h, const void* images, int img_fmt, const float* K0, const float* K1, int n_pairs, int H, int W,
+                       unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
+                       float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
+                       int* status, void* ws, long long ws_bytes, void* stream) {
   Workspace w;
   MK_TRY(check_ws(h, n_pairs, H, W, ws, ws_bytes, w));
   const Geo g = make_geo(n_pairs, H, W);
   cudaStream_t st = (cudaStream_t)stream;
-  MK_TRY(run_extract(h, images, n_pairs, H, W, kps, depth, scr, dsc, w, st));
+  MK_TRY(run_extract(h, images, img_fmt, n_pairs, H, W, kps, depth, scr, dsc, w, st));
   MK_TRY(run_match(h, n_pairs, g.N, scores, kp_scores, final_scores, w, st));
   return run_solve(h, final_scores, kps, depth, K0, K1, n_pairs, g.N, seed, nullptr, nullptr, pose, best_set, inl_mask,
                    sampled_out, nullptr, status, w, st);
+}
+
+int mk_forward(mk_handle* h, const float* images, const float* K0, const float* K1, int n_pairs, int H, int W,
+               unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
+               float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
+               int* status, void* ws, long long ws_bytes, void* stream) {
+  return forward_any(h, images, 0, K0, K1, n_pairs, H, W, seed, kps, depth, scr, dsc, scores, kp_scores, final_scores, pose,
+                     best_set, inl_mask, sampled_out, status, ws, ws_bytes, stream);
+}
+
+int mk_forward_u8(mk_handle* h, const unsigned char* images, const float* K0, const float* K1, int n_pairs, int H, int W,
+                  unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
+                  float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
+                  int* status, void* ws, long long ws_bytes, void* stream) {
+  return forward_any(h, images, 1, K0, K1, n_pairs, H, W, seed, kps, depth, scr, dsc, scores, kp_scores, final_scores, pose,
+                     best_set, inl_mask, sampled_out, status, ws, ws_bytes, stream);
+}
+
+int mk_pose_to_submission(const float* pose, int n_pairs, double* out, void* stream) {
+  if (!pose || !out || n_pairs < 0) { set_last_error("null argument"); return MK_ERR_INVALID; }
+  return pose_to_submission(pose, n_pairs, out, (cudaStream_t)stream);
 }
 
 long long mk_launch_count(mk_handle* h) { return h ? h->launches : -1; }
@@ -606,6 +639,10 @@ int mk_op_gemm(const mk_gemm_args* a, void* stream) {
 int mk_op_patch_gather(const float* img, void* P, int n_img, int H, int W, int kpad, float* X, const float* cls_pos,
                        int D, void* stream) {
   return patch_gather(img, P, n_img, H, W, kpad, X, cls_pos, D, (cudaStream_t)stream);
+}
+int mk_op_ingest_u8(const unsigned char* img, void* P, int n_img, int H, int W, int kpad, float* X, const float* cls_pos,
+                    int D, void* stream) {
+  return ingest_u8(img, P, n_img, H, W, kpad, X, cls_pos, D, (cudaStream_t)stream);
 }
 int mk_op_layernorm(const float* x, const float* w, const float* b, void* out, int rows, int D, float eps, int mode,
                     int gh, int gw, void* stream) {

@@ -185,11 +185,10 @@ static bool use_simt() {
 
 template <int BN, int EPI, int STAGES>
 static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
+  static unsigned long long attr_mask = 0;
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
-  if (!attr_set) {
+  if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   MK_CUDA_CHECK(launch_k(gemm_tc_kernel<BN, EPI, STAGES>, grid, dim3(GEMM_THREADS), (size_t)smem, stream, tmA, tmB, p));
   return MK_OK;
@@ -198,11 +197,10 @@ static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, 
 // EPI_RESID_LN: the grid.y CTAs of a row of tiles form one thread-block cluster (row statistics through DSMEM)
 template <int BN, int EPI, int STAGES>
 static int launch_tc_cluster(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
+  static unsigned long long attr_mask = 0;
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
-  if (!attr_set) {
+  if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -230,18 +228,20 @@ static int wide_min_pct() {   // 128 x 256 tiles when at least this many (in % o
 }
 
 static int sm_count() {
-  static int n = 0;
-  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-  return n;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = n[dev & 63];
+  if (!c) { cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev); if (c <= 0) c = 148; }
+  return c;
 }
 
 template <int BN, int EPI>
 static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
+  static unsigned long long attr_mask = 0;
   constexpr int smem = gemm_persistent_smem_bytes<BN>();
-  if (!attr_set) {
+  if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   const int sms = sm_count();
   const long long total = (long long)tiles.x * tiles.y * tiles.z;
@@ -260,11 +260,10 @@ static bool two_sm_enabled() {
 
 template <int EPI>
 static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
+  static unsigned long long attr_mask = 0;
   constexpr int smem = gemm_2sm_smem_bytes();
-  if (!attr_set) {
+  if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   const long long total = (long long)tiles256.x * tiles256.y * tiles256.z;
   const long long pairs = sm_count() / 2;

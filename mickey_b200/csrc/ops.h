@@ -11,6 +11,10 @@ int attention(const void* qkv, void* out, int n_img, int T, int D, int heads, cu
 int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s);   // tcgen05 / TMEM version
 int attention_dispatch(const void* qkv, void* out, int n_img, int T, int D, int heads, int impl, cudaStream_t s);
 
+// io_ops.cu (the steps either side of the path: image ingest, submission packing)
+int ingest_u8(const uint8_t* img, void* P, int n_img, int H, int W, int kpad, float* X, const float* cls_pos, int D, cudaStream_t s);
+int pose_to_submission(const float* pose, int n, double* out, cudaStream_t s);
+
 // head_ops.cu
 int linattn_kv_chunks(int h2, int w2);
 int linattn_kv(const float* qkv, float* kv_part, float* kv, int n_img, int G, int h2, int w2, cudaStream_t s);

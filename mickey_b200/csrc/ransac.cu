@@ -853,11 +853,10 @@ int ransac_solve(const float* final_scores, const float* kps0, const float* d0, 
   MK_CUDA_CHECK(cudaGetLastError());
   const int hyp_per_block = 8;
   const size_t smem_h = (size_t)7 * n_s * 4, smem_f = (size_t)6 * n_s * 4;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MK_CUDA_CHECK(cudaFuncSetAttribute(ransac_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   if (smem_h > 200 * 1024) { set_last_error("NUM_SAMPLED_MATCHES too large for shared memory"); return MK_ERR_UNSUPPORTED; }
   MK_CUDA_CHECK(launch_k(ransac_hyp_kernel, dim3(ceil_div(IR, hyp_per_block), IM, B), dim3(HYP_THREADS), smem_h, st,

@@ -181,6 +181,7 @@ def sine_table_padded(gh: int, gw: int, d_model: int = 128) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------
 class Engine:
     """One C handle + packed weights + workspace for a fixed (cfg, device)."""
+    MAX_GEOMETRIES = 4          # image geometries whose tables / workspace / graphs are kept alive at once
 
     def __init__(self, cfg, device, side_stream: bool = False):
         """side_stream=True gives the engine its own CUDA stream for forward(): two such engines (see
@@ -202,6 +203,11 @@ class Engine:
         self.geo = None
         self.ws = None
         self.ws_pairs = 0
+        # Per-geometry state (size-dependent tables, workspace, captured graphs) stays alive while graphs that baked
+        # its pointers may still be replayed; a weight (re)load drops all of it.
+        self._geo_state: Dict[tuple, dict] = {}
+        self._graphs, self._slot = {}, {}
+        self._copy_stream = None
 
     def __del__(self):
         try:
@@ -225,7 +231,13 @@ class Engine:
                                  sd[BACKBONE + "patch_embed.proj.bias"].detach().to(self.device).float())
         for name, t in self.packed.items():
             self._register(name, t)
+        # captured graphs hold raw pointers of the previous packed weights and tables: none of them may be replayed
+        self._graphs.clear()
+        self._slot.clear()
+        self._geo_state.clear()
         self.geo = None
+        self.ws = None
+        self.ws_pairs = 0
 
     def _register(self, name, t):
         assert t.is_contiguous() and t.device == self.device
@@ -236,18 +248,29 @@ class Engine:
         """Size-dependent tables + workspace for images cropped to (H, W) (multiples of 14)."""
         assert self.packed, "load_state_dict first"
         if self.geo != (H, W):
-            gh, gw = H // PATCH, W // PATCH
-            with torch.no_grad():
-                pos, cls, pbias = self._raw_pos
-                full = interpolate_pos_embed(pos, gh, gw)
-                self.packed["patch.posb"] = (full[1:] + pbias[None]).contiguous()
-                self.packed["patch.clspos"] = (cls.reshape(-1) + full[0]).contiguous()
-                self.packed["head.pe"] = sine_table_padded(gh, gw).to(self.device)
+            if self.geo is not None:                       # park the outgoing geometry's workspace with its state
+                self._geo_state[self.geo].update(ws=self.ws, ws_pairs=self.ws_pairs)
+            gs = self._geo_state.get((H, W))
+            if gs is None:
+                gh, gw = H // PATCH, W // PATCH
+                with torch.no_grad():
+                    pos, cls, pbias = self._raw_pos
+                    full = interpolate_pos_embed(pos, gh, gw)
+                    gs = {"patch.posb": (full[1:] + pbias[None]).contiguous(),
+                          "patch.clspos": (cls.reshape(-1) + full[0]).contiguous(),
+                          "head.pe": sine_table_padded(gh, gw).to(self.device), "ws": None, "ws_pairs": 0}
+                if len(self._geo_state) >= self.MAX_GEOMETRIES:      # evict the oldest geometry together with its graphs
+                    old = next(iter(self._geo_state))
+                    del self._geo_state[old]
+                    for k in [k for k in self._graphs if (k[1], k[2]) == old]:
+                        del self._graphs[k]
+                self._geo_state[(H, W)] = gs
             for n in ("patch.posb", "patch.clspos", "head.pe"):
-                self._register(n, self.packed[n])
+                self.packed[n] = gs[n]
+                self._register(n, gs[n])
             _lib.check(self.lib.mk_finalize(self.h, H, W), "mk_finalize")
             self.geo = (H, W)
-            self.ws = None
+            self.ws, self.ws_pairs = gs["ws"], gs["ws_pairs"]
         if self.ws is None or self.ws_pairs < n_pairs:
             nbytes = self.lib.mk_workspace_bytes(self.h, n_pairs, H, W)
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -308,8 +331,14 @@ class Engine:
         """images fp32 [2B, 3, H, W] (image0 batch then image1 batch) -> kps, depth, scr, dsc.
         H, W need not be multiples of 14: the patch gather reads only the top-left 14*(H//14) x 14*(W//14) crop
         (reference mickey_extractor.py:46), so no cropped copy is made."""
-        images = images.float().contiguous()
-        n_img, _, H, W = images.shape
+        u8 = images.dtype == torch.uint8
+        if u8:                                           # [2B, H, W, 3] RGB as decoded (mk_extract_u8, SURVEY.md §8 f1)
+            assert images.dim() == 4 and images.shape[-1] == 3, "uint8 images must be [n, H, W, 3] (HWC, RGB)"
+            images = images.contiguous()
+            n_img, H, W, _ = images.shape
+        else:
+            images = images.float().contiguous()
+            n_img, _, H, W = images.shape
         assert n_img % 2 == 0
         B, N = n_img // 2, (H // PATCH) * (W // PATCH)
         ws = self._ws_for(B, H, W)
@@ -318,8 +347,9 @@ class Engine:
         depth = torch.empty(n_img, 1, N, device=dev)
         scr = torch.empty(n_img, 1, N, device=dev)
         dsc = torch.empty(n_img, self.mkcfg.desc_dim, N, device=dev)
-        _lib.check(self.lib.mk_extract(self.h, _lib.ptr(images), B, H, W, _lib.ptr(kps), _lib.ptr(depth), _lib.ptr(scr),
-                                       _lib.ptr(dsc), _lib.ptr(ws), ws.numel(), self._stream()), "mk_extract")
+        fn = self.lib.mk_extract_u8 if u8 else self.lib.mk_extract
+        _lib.check(fn(self.h, _lib.ptr(images), B, H, W, _lib.ptr(kps), _lib.ptr(depth), _lib.ptr(scr),
+                      _lib.ptr(dsc), _lib.ptr(ws), ws.numel(), self._stream()), "mk_extract")
         return kps, depth, scr, dsc
 
     def match(self, B: int, N: int):
@@ -332,12 +362,13 @@ class Engine:
         return scores, kp_scores, final
 
     # -- whole path in one C call, optionally replayed from a CUDA graph -------------------------------------------
-    def _static_buffers(self, B, H, W):
+    def _static_buffers(self, B, H, W, u8=False):
         dev, c = self.device, self.mkcfg
         N = (H // PATCH) * (W // PATCH)
         f = lambda *s: torch.empty(*s, device=dev)                       # noqa: E731
         return {
-            "images": f(2 * B, 3, H, W), "K0": f(B, 3, 3), "K1": f(B, 3, 3),
+            "images": torch.empty(2 * B, H, W, 3, dtype=torch.uint8, device=dev) if u8 else f(2 * B, 3, H, W),
+            "K0": f(B, 3, 3), "K1": f(B, 3, 3),
             "kps": f(2 * B, 2, N), "depth": f(2 * B, 1, N), "scr": f(2 * B, 1, N), "dsc": f(2 * B, c.desc_dim, N),
             "scores": f(B, N, N), "kp_scores": f(B, N, N), "final_scores": f(B, N, N), "pose": f(B, 13),
             "best_set": torch.empty(B, dtype=torch.int32, device=dev), "inlier_mask": f(B, c.num_sampled),
@@ -347,7 +378,8 @@ class Engine:
 
     def _call_forward(self, st, B, H, W, seed):
         ws = self.ws
-        _lib.check(self.lib.mk_forward(
+        fn = self.lib.mk_forward_u8 if st["images"].dtype == torch.uint8 else self.lib.mk_forward
+        _lib.check(fn(
             self.h, _lib.ptr(st["images"]), _lib.ptr(st["K0"]), _lib.ptr(st["K1"]), B, H, W, C.c_ulonglong(seed),
             _lib.ptr(st["kps"]), _lib.ptr(st["depth"]), _lib.ptr(st["scr"]), _lib.ptr(st["dsc"]), _lib.ptr(st["scores"]),
             _lib.ptr(st["kp_scores"]), _lib.ptr(st["final_scores"]), _lib.ptr(st["pose"]), _lib.ptr(st["best_set"]),
@@ -362,16 +394,25 @@ class Engine:
         inputs are copied H2D on a side stream into the other buffer set while the previous call is still
         computing; device inputs are copied D2D on the main stream."""
         B = image0.shape[0]
-        H, W = image0.shape[-2], image0.shape[-1]
+        u8 = image0.dtype == torch.uint8                 # [B, H, W, 3] RGB straight from the decoder (mk_forward_u8)
+        if u8:
+            if image0.dim() != 4 or image0.shape[-1] != 3 or image1.dtype != torch.uint8:
+                raise _lib.MickeyB200Error("uint8 images must both be [B, H, W, 3] (HWC, RGB)")
+            H, W = image0.shape[1], image0.shape[2]
+        else:
+            H, W = image0.shape[-2], image0.shape[-1]
+        if image1.shape != image0.shape:
+            raise _lib.MickeyB200Error(f"image0 {tuple(image0.shape)} and image1 {tuple(image1.shape)} must have the same shape: "
+                                       "both images of a batch go through one extraction call")
         self._ws_for(B, H, W)
-        if not hasattr(self, "_graphs"):
-            self._graphs, self._slot, self._copy_stream = {}, {}, torch.cuda.Stream(device=self.device)
-        slot = self._slot.get((B, H, W), 0)
-        self._slot[(B, H, W)] = slot ^ 1
-        key = (B, H, W, slot)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        slot = self._slot.get((B, H, W, u8), 0)
+        self._slot[(B, H, W, u8)] = slot ^ 1
+        key = (B, H, W, slot, u8)
         ent = self._graphs.get(key)
         if ent is None or ent["ws_ptr"] != self.ws.data_ptr():
-            ent = {"st": self._static_buffers(B, H, W), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(),
+            ent = {"st": self._static_buffers(B, H, W, u8), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(),
                    "calls": 0, "done": None}
             self._graphs[key] = ent
         st = ent["st"]

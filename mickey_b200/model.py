@@ -24,6 +24,15 @@ from .weights import synthetic_state_dict
 _BUFFER_SUFFIXES = ("running_mean", "running_var", "num_batches_tracked")
 
 
+def synthetic_backbone_allowed() -> bool:
+    """Benchmarks and tests run on seeded random-init weights (BASELINE.json: there is no network for the DINOv2
+    download the reference performs, mickey_extractor.py:15-17); they opt in with MICKEY_SYNTHETIC_BACKBONE=1.
+    Anyone else loading a real mickey.ckpt (which omits the frozen DINOv2 tensors) without supplying DINOv2 weights
+    would silently get poses from a random backbone, so that is an error."""
+    import os
+    return os.environ.get("MICKEY_SYNTHETIC_BACKBONE", "0") == "1"
+
+
 class _ParamTree(nn.Module):
     """A module whose only job is to hold tensors under dotted names."""
 
@@ -112,6 +121,9 @@ class ComputeCorrespondences(nn.Module):
         eng = self._owner._engine()
         im0, im1 = data["image0"], data["image1"]
         B = im0.shape[0]
+        if im0.shape != im1.shape:
+            raise ValueError(f"image0 {tuple(im0.shape)} and image1 {tuple(im1.shape)} must have the same shape (both images "
+                             "of a batch are extracted in one call)")
         images = torch.cat([im0, im1], dim=0)
         kps, depth, scr, dsc = eng.extract(images)
         N = kps.shape[-1]
@@ -153,6 +165,7 @@ class MickeyRelativePose(nn.Module):
             self.compute_matches.__getattr__(name.split(".")[1]).add(".".join(name.split(".")[2:]), t)
         import os
         dinov2_weights = dinov2_weights or os.environ.get("MICKEY_DINOV2_WEIGHTS")
+        self.__dict__["_backbone_is_synthetic"] = dinov2_weights is None
         if dinov2_weights is not None:
             if isinstance(dinov2_weights, str):
                 dinov2_weights = torch.load(dinov2_weights, map_location="cpu")
@@ -169,6 +182,15 @@ class MickeyRelativePose(nn.Module):
 
     # -- checkpoint plumbing (compute_pose.py:39-48, builder.py:11-13) ---------------------------------------
     def on_load_checkpoint(self, checkpoint):
+        """compute_pose.py:39-48: the checkpoint's (absent) DINOv2 tensors are filled from the module's own backbone.
+        The reference's own backbone is the downloaded pretrained DINOv2; here it must have been supplied
+        (`dinov2_weights=` / $MICKEY_DINOV2_WEIGHTS) unless synthetic weights were explicitly allowed."""
+        if self.__dict__.get("_backbone_is_synthetic", True) and not synthetic_backbone_allowed():
+            raise RuntimeError(
+                "MickeyRelativePose holds seeded RANDOM DINOv2 weights: the reference downloads the pretrained ViT at this "
+                "point (mickey_extractor.py:15-17) and there is no network here.  Pass dinov2_weights= (or set "
+                "$MICKEY_DINOV2_WEIGHTS to a dinov2_vit*14_pretrain.pth), or set MICKEY_SYNTHETIC_BACKBONE=1 to run on "
+                "synthetic weights on purpose (benchmarks / tests).")
         own = self.compute_matches.state_dict()
         for k in own:
             if "dinov2" in k:
@@ -254,7 +276,9 @@ class MickeyRelativePose(nn.Module):
         im0, im1 = data["image0"], data["image1"]
         B = im0.shape[0]
         seed = int(torch.randint(1, 2 ** 62, (1,)).item())
-        st = eng.forward(im0.float(), im1.float(), data["K_color0"].float(), data["K_color1"].float(), seed,
+        if im0.dtype != torch.uint8:                     # uint8 [B,H,W,3] goes to the ingest kernel as it is (mickey_b200.io)
+            im0, im1 = im0.float(), im1.float()
+        st = eng.forward(im0, im1, data["K_color0"].float(), data["K_color1"].float(), seed,
                          use_graph=getattr(self, "use_graph", True))
         keep = (lambda t: t) if getattr(self, "static_outputs", False) else (lambda t: t.clone())
         H, W = eng.geo

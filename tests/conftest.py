@@ -4,6 +4,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("MICKEY_SYNTHETIC_BACKBONE", "1")      # tests run on seeded random-init weights on purpose
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

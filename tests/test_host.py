@@ -56,6 +56,26 @@ def test_state_dict_names_roundtrip():
                "K_color0": torch.eye(3)[None], "K_color1": torch.eye(3)[None]})
 
 
+def test_real_checkpoint_without_dinov2_weights_is_an_error(monkeypatch):
+    """A real mickey.ckpt omits the frozen DINOv2 tensors; the reference fills them from its downloaded backbone.  Without
+    supplied DINOv2 weights our module only holds seeded random values, which must not be used silently."""
+    from mickey_b200.model import MickeyRelativePose
+    cfg = mickey_cfg("vits", 2, 4)
+    ck = synthetic_checkpoint(cfg, seed=4, with_backbone=False)
+    monkeypatch.setenv("MICKEY_SYNTHETIC_BACKBONE", "0")
+    with pytest.raises(RuntimeError, match="RANDOM DINOv2"):
+        MickeyRelativePose(cfg).on_load_checkpoint(ck)
+    # supplying DINOv2 weights (native names, as in dinov2_vit*14_pretrain.pth) is the supported way
+    pre = "compute_matches.extractor.dinov2_vitl14."
+    dino = {k[len(pre):]: v for k, v in synthetic_state_dict(cfg, seed=9).items() if k.startswith(pre)}
+    model = MickeyRelativePose(cfg, dinov2_weights=dino)
+    model.on_load_checkpoint(ck)
+    model.load_state_dict(ck["state_dict"], strict=True)
+    assert torch.equal(model.state_dict()[pre + "blocks.3.attn.qkv.weight"], dino["blocks.3.attn.qkv.weight"])
+    monkeypatch.setenv("MICKEY_SYNTHETIC_BACKBONE", "1")
+    MickeyRelativePose(cfg).on_load_checkpoint(synthetic_checkpoint(cfg, seed=4, with_backbone=False))
+
+
 def test_pack_weights_shapes_and_bn_fold():
     cfg = mickey_cfg("vits", 2, 4)
     sd = synthetic_state_dict(cfg, seed=0)
