@@ -79,7 +79,8 @@ int mk_extract_u8(mk_handle* h, const unsigned char* images_u8_dev, int n_pairs,
  * replaces featureMatcher/dualSoftmax.forward (feature_matcher.py:48-83), kp_matrix_scores
  * (compute_correspondences.py:46-50) and `final_scores = scores * kp_scores` (compute_pose.py:23).
  * Uses the descriptors/scores left in the workspace by mk_extract.  Outputs fp32 [n_pairs, N, N];
- * scores_dev / kp_scores_dev may be NULL ("lean" mode: only final_scores is materialised). */
+ * scores_dev AND kp_scores_dev may both be NULL ("lean" mode: only final_scores, the one matrix the solver reads, is
+ * materialised: 17 instead of 47 MB per 720x540 pair); the same holds for mk_forward / mk_forward_u8. */
 int mk_match(mk_handle* h, int n_pairs, float* scores_dev, float* kp_scores_dev, float* final_scores_dev,
              void* ws_dev, long long ws_bytes, void* stream);
 
@@ -135,7 +136,7 @@ int mk_profile_read(mk_handle* h, char* buf, int buf_bytes);
 
 /* ---- operator-level entry points (unit tests of single kernels; not needed by an integrator) ---- */
 typedef struct mk_gemm_args {
-  int epi;                 /* 0 STORE_H, 1 RESID_F, 2 PATCH, 3 CONV, 4 STORE_F, 5 LN, 6 LSE, 7 DUAL,
+  int epi;                 /* 0 STORE_H, 1 RESID_F, 2 PATCH, 3 CONV, 4 STORE_F, 5 LN, 6 LSE (row + column partials), 7 DUAL,
                               8 RESID_LN (RESID_F, then out_h = LayerNorm(out_f row) * aux + beta; N <= 1024) */
   int impl;                /* 0 default (tcgen05), 1 tcgen05, 2 SIMT debug kernel */
   const void* a; long long a_rows, a_cols, a_ld;
@@ -153,8 +154,11 @@ typedef struct mk_gemm_args {
   int pad_h2, pad_w2, tok_per_img;
   float eps;
   int n_valid; float inv_temp;
-  const float* shift; const float* dustbin; float* row_sum;   /* LSE out: [groups, n_valid, 2*ceil(n_valid/128)] partial sums */
-  const float* rs; const float* cs; const float* scr0; const float* scr1;
+  const float* dustbin;
+  float* part_row; float* part_col; int part_ld;   /* LSE out: float2 (max, sum) partials, [groups][part_ld/64 | part_ld/32 slots][part_ld];
+                                                      part_ld = n_valid rounded up to 128 */
+  const float* lse_r; const float* lse_c;          /* DUAL in: log2-domain log-sum-exp per row / column, [groups, part_ld] (mk_op_matcher_reduce) */
+  const float* scr0; const float* scr1;
   float* scores; float* kp_scores; float* final_scores;
 } mk_gemm_args;
 
@@ -171,6 +175,8 @@ int mk_op_attention(const void* qkv_h, void* out_h, int n_img, int T, int D, int
 /* kv_part_f: scratch [n_img, G, ceil(h2*w2/32), 8, 272] fp32 */
 int mk_op_linattn(const float* qkv_f, float* kv_part_f, float* kv_f, void* msg_h, int n_img, int G, int h2, int w2, float eps,
                   void* stream);
+int mk_op_matcher_reduce(const float* part_row, const float* part_col, const float* dustbin, int B, int N, int part_ld,
+                         float* lse_r, float* lse_c, void* stream);
 int mk_op_sample(const float* final_scores, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
                  long long ws_bytes, int* idx_out, int* status, void* stream);
 long long mk_op_sample_workspace_bytes(int B, int IM);

@@ -46,8 +46,9 @@ class MkGemmArgs(C.Structure):
         ("pad_h2", C.c_int), ("pad_w2", C.c_int), ("tok_per_img", C.c_int),
         ("eps", C.c_float),
         ("n_valid", C.c_int), ("inv_temp", C.c_float),
-        ("shift", C.c_void_p), ("dustbin", C.c_void_p), ("row_sum", C.c_void_p),
-        ("rs", C.c_void_p), ("cs", C.c_void_p), ("scr0", C.c_void_p), ("scr1", C.c_void_p),
+        ("dustbin", C.c_void_p),
+        ("part_row", C.c_void_p), ("part_col", C.c_void_p), ("part_ld", C.c_int),
+        ("lse_r", C.c_void_p), ("lse_c", C.c_void_p), ("scr0", C.c_void_p), ("scr1", C.c_void_p),
         ("scores", C.c_void_p), ("kp_scores", C.c_void_p), ("final_scores", C.c_void_p),
     ]
 
@@ -94,6 +95,7 @@ EXPORTS = {
                                   C.c_int, C.c_int, C.c_void_p]),
     "mk_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mk_op_linattn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "mk_op_matcher_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mk_op_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_void_p, C.c_longlong,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "mk_op_sample_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int]),

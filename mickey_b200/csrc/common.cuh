@@ -25,8 +25,8 @@ enum Epi : int {
   EPI_CONV    = 3,   // out_h = mask(act(acc + bias + res_h) + aux)       (3x3 / 1x1 conv, BN folded, shortcut, PE)
   EPI_STORE_F = 4,   // out_f = acc                        fp32           (linear-attention q,k,v)
   EPI_LN      = 5,   // out = LN_128(acc) [+ out_f]        fp16 (+fp32)   (merge+norm1, mlp.2+norm2+residual)
-  EPI_LSE     = 6,   // row_sum[m] += sum_n exp(acc/T - shift)            (matcher pass 1)
-  EPI_DUAL    = 7,   // scores / kp_scores / final_scores                 (matcher pass 2)
+  EPI_LSE     = 6,   // per-tile (max, sum exp) partials of every row AND every column of S/T   (matcher pass 1)
+  EPI_DUAL    = 7,   // scores = exp(2 S/T - lse_row - lse_col), kp_scores, final_scores          (matcher pass 2)
   EPI_RESID_LN = 8,  // EPI_RESID_F, then out_h = LN_N(out_f row) * aux + beta   (attn.proj + norm2, mlp.fc2 + next norm1):
                      // the N/128 CTAs of a row of tiles form a thread-block cluster and exchange row statistics
                      // through distributed shared memory (N <= 1024)
@@ -57,11 +57,15 @@ struct GemmParams {
   // matcher
   int n_valid;              // valid rows == valid cols per pair
   float inv_temp;
-  const float* shift;       // [groups] softmax shift per pair
   const float* dustbin;     // device scalar or nullptr
-  float* row_sum;           // EPI_LSE out: partial sums [groups, n_valid, sum_slots] (slot = 2*n_tile + warp half)
-  int sum_slots;            // 2 * ceil(n_valid / 128)
-  const float* rs; const float* cs;     // EPI_DUAL in: the two partial-sum arrays (rows of S, rows of S^T)
+  // EPI_LSE out: online-softmax partials in the log2 domain, float2 (max, sum 2^(x - max)) per slot:
+  //   part_row[(g * 2*tiles + 2*n_tile + half) * part_ld + row]   (a warp's 64 columns of one row)
+  //   part_col[(g * 4*tiles + 4*m_tile + q)    * part_ld + col]   (a warp's 32 rows of one column)
+  // with tiles = part_ld / 128.  Slot-major, so that both the warps' stores and the reduce kernel's loads coalesce.
+  float2* part_row; float2* part_col;
+  int part_ld;              // n_valid rounded up to a multiple of 128
+  // EPI_DUAL in: log2-domain log-sum-exp of every row / column of the dustbin-augmented S/T, [groups, part_ld]
+  const float* lse_r; const float* lse_c;
   const float* scr0; const float* scr1; // [groups, n_valid]
   float* scores; float* kp_scores; float* final_scores;   // [groups, n_valid, n_valid]
 };

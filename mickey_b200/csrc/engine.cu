@@ -67,7 +67,7 @@ struct Workspace {
   // head outputs kept for the matcher
   float* score_raw; __half* DSCX; float* nrm2; float* scr_copy;
   // matcher
-  float *shift, *row_sum, *col_sum;
+  float *part_row, *part_col, *lse_r, *lse_c;
   // solver
   void* samp_ws; int* idx; float* xyw; float* hyp_scores; float* hyp_Rt; int* status; int* best_hyp;
   size_t bytes;
@@ -98,9 +98,9 @@ Workspace carve(void* base, const mk_config& c, const Geo& g, int n_pairs) {
   w.DSCX = cv.take<__half>((size_t)g.n_img * g.N * 384);
   w.nrm2 = cv.take<float>((size_t)g.n_img * g.N);
   w.scr_copy = cv.take<float>((size_t)g.n_img * g.N);
-  w.shift = cv.take<float>(n_pairs);
-  const size_t slots = 2 * (size_t)ceil_div(g.N, 128);
-  w.row_sum = cv.take<float>((size_t)n_pairs * g.N * slots); w.col_sum = cv.take<float>((size_t)n_pairs * g.N * slots);
+  const size_t npad = (size_t)ceil_div(g.N, 128) * 128;          // matcher: float2 partials [pair][slot][npad], lse vectors [pair][npad]
+  w.part_row = cv.take<float>((size_t)n_pairs * (npad / 64) * npad * 2); w.part_col = cv.take<float>((size_t)n_pairs * (npad / 32) * npad * 2);
+  w.lse_r = cv.take<float>((size_t)n_pairs * npad); w.lse_c = cv.take<float>((size_t)n_pairs * npad);
   const size_t streams = (size_t)n_pairs * c.it_matches;
   w.samp_ws = cv.take<uint8_t>(sampler_workspace_bytes(n_pairs, c.it_matches));
   w.idx = cv.take<int>(streams * c.num_sampled);
@@ -351,24 +351,25 @@ int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores,
   Lookup L{h};
   const float* dust = c.use_dustbin ? L.f("dustbin", 1) : nullptr;
   if (!L.ok) return MK_ERR_MISSING_TENSOR;
-  if (!scores || !kp_scores || !final_scores) {
-    set_last_error("mk_match: lean mode (NULL scores/kp_scores) is not implemented yet");
-    return MK_ERR_UNSUPPORTED;
+  if (!final_scores || ((scores == nullptr) != (kp_scores == nullptr))) {
+    set_last_error("mk_match: final_scores is required; scores and kp_scores are given together or both NULL (lean mode)");
+    return MK_ERR_INVALID;
   }
   const float inv_t = 1.0f / c.temperature;
-  MK_KERNEL("match.prep", matcher_prep(w.nrm2, dust, inv_t, w.shift, n_pairs, N, st));
   const __half* A0 = w.DSCX;                                   // role-0 descriptors [n_pairs*N, 384]
   const __half* A1 = w.DSCX + (size_t)n_pairs * N * 384;       // role-1 descriptors
   const long long rows = (long long)n_pairs * N;
+  const int npad = ceil_div(N, 128) * 128;
   auto mp = [&]() {
     GemmParams p = base_params(N, N, 384);
-    p.groups = n_pairs; p.a_row_group_off = N; p.b_row_group_off = N; p.n_valid = N; p.inv_temp = inv_t;
-    p.shift = w.shift; p.dustbin = dust; p.sum_slots = 2 * ceil_div(N, 128);
+    p.groups = n_pairs; p.a_row_group_off = N; p.b_row_group_off = N; p.n_valid = N; p.inv_temp = inv_t; p.part_ld = npad;
     return p;
   };
-  { GemmParams p = mp(); p.row_sum = w.row_sum; MK_TRY(gemm(h, "match.lse", EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
-  { GemmParams p = mp(); p.row_sum = w.col_sum; MK_TRY(gemm(h, "match.lse", EPI_LSE, A1, rows, 384, A0, rows, 384, p, st)); }
-  { GemmParams p = mp(); p.rs = w.row_sum; p.cs = w.col_sum; p.scr0 = w.scr_copy; p.scr1 = w.scr_copy + (size_t)n_pairs * N;
+  // pass 1: S once, row and column partials from the same tile; then the tiny fold (+ dustbin); pass 2: outputs
+  { GemmParams p = mp(); p.part_row = reinterpret_cast<float2*>(w.part_row); p.part_col = reinterpret_cast<float2*>(w.part_col);
+    MK_TRY(gemm(h, "match.lse", EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
+  MK_KERNEL("match.reduce", matcher_lse_reduce(w.part_row, w.part_col, dust, n_pairs, N, npad, w.lse_r, w.lse_c, st));
+  { GemmParams p = mp(); p.lse_r = w.lse_r; p.lse_c = w.lse_c; p.scr0 = w.scr_copy; p.scr1 = w.scr_copy + (size_t)n_pairs * N;
     p.scores = scores; p.kp_scores = kp_scores; p.final_scores = final_scores;
     MK_TRY(gemm(h, "match.dual_softmax", EPI_DUAL, A0, rows, 384, A1, rows, 384, p, st)); }
   return MK_OK;
@@ -575,7 +576,7 @@ long long mk_workspace_offset(mk_handle* h, const char* name, int n_pairs, int H
       {"S1", w.S1}, {"O1", w.O1}, {"T2", w.T2}, {"S2", w.S2}, {"O2", w.O2}, {"T3", w.T3}, {"S3", w.S3}, {"CAT", w.CAT},
       {"MSG", w.MSG}, {"HM", w.HM}, {"T4k", w.T4k}, {"S4k", w.S4k}, {"T4d", w.T4d}, {"X32", w.X32}, {"QKV32", w.QKV32},
       {"KV", w.KV}, {"Y4k", w.Y4k}, {"Y4d", w.Y4d}, {"score_raw", w.score_raw}, {"DSCX", w.DSCX}, {"nrm2", w.nrm2},
-      {"row_sum", w.row_sum}, {"col_sum", w.col_sum}, {"idx", w.idx}, {"xyw", w.xyw}, {"hyp_scores", w.hyp_scores},
+      {"lse_r", w.lse_r}, {"lse_c", w.lse_c}, {"idx", w.idx}, {"xyw", w.xyw}, {"hyp_scores", w.hyp_scores},
       {"hyp_Rt", w.hyp_Rt}};
   auto it = m.find(name);
   if (it == m.end()) { set_last_error("unknown workspace buffer '%s'", name); return -1; }
@@ -628,9 +629,9 @@ int mk_op_gemm(const mk_gemm_args* a, void* stream) {
   p.out_h = (__half*)a->out_h; p.out_h_ld = a->out_h_ld; p.out_h_group_off = a->out_h_group_off;
   p.res_h = (const __half*)a->res_h; p.res_h_ld = a->res_h_ld; p.res_h_group_off = a->res_h_group_off;
   p.aux = a->aux; p.aux_group_mask = a->aux_group_mask; p.pad_h2 = a->pad_h2; p.pad_w2 = a->pad_w2; p.tok_per_img = a->tok_per_img;
-  p.eps = a->eps; p.n_valid = a->n_valid; p.inv_temp = a->inv_temp; p.shift = a->shift; p.dustbin = a->dustbin;
-  p.sum_slots = 2 * ceil_div(a->n_valid > 0 ? a->n_valid : 1, 128);
-  p.row_sum = a->row_sum; p.rs = a->rs; p.cs = a->cs; p.scr0 = a->scr0; p.scr1 = a->scr1;
+  p.eps = a->eps; p.n_valid = a->n_valid; p.inv_temp = a->inv_temp; p.dustbin = a->dustbin;
+  p.part_row = reinterpret_cast<float2*>(a->part_row); p.part_col = reinterpret_cast<float2*>(a->part_col); p.part_ld = a->part_ld;
+  p.lse_r = a->lse_r; p.lse_c = a->lse_c; p.scr0 = a->scr0; p.scr1 = a->scr1;
   p.scores = a->scores; p.kp_scores = a->kp_scores; p.final_scores = a->final_scores;
   GemmOperand A{a->a, a->a_rows, a->a_cols, a->a_ld}, B{a->b, a->b_rows, a->b_cols, a->b_ld};
   return launch_gemm(a->epi, A, B, p, (cudaStream_t)stream, a->impl);
@@ -655,6 +656,10 @@ int mk_op_linattn(const float* qkv, float* kv_part, float* kv, void* msg, int n_
                   void* stream) {
   MK_TRY(linattn_kv(qkv, kv_part, kv, n_img, Gn, h2, w2, (cudaStream_t)stream));
   return linattn_msg(qkv, kv, msg, n_img, Gn, h2, w2, eps, (cudaStream_t)stream);
+}
+int mk_op_matcher_reduce(const float* part_row, const float* part_col, const float* dustbin, int B, int N, int part_ld,
+                         float* lse_r, float* lse_c, void* stream) {
+  return matcher_lse_reduce(part_row, part_col, dustbin, B, N, part_ld, lse_r, lse_c, (cudaStream_t)stream);
 }
 long long mk_op_sample_workspace_bytes(int B, int IM) { return (long long)sampler_workspace_bytes(B, IM) + 512; }
 int mk_op_sample(const float* fs, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,

@@ -354,80 +354,96 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
   }
 }
 
-// ---- whole-row epilogues (accumulated across the chunks of one tile) ------------------------------
-// EPI_LSE: partial sum over this tile's valid columns of exp(S/T - shift)
-__device__ __forceinline__ float lse_partial(const GemmParams& p, int g, int n0, const float (&v)[32]) {
-  const float L2E = 1.4426950408889634f;
-  const float sh = __ldg(p.shift + g) * L2E;
-  const float k2 = p.inv_temp * L2E;
-  float s = 0.0f;
+// ---- matcher epilogues (reference modules/utils/feature_matcher.py:64-83) -----------------------------------
+// softmax(dim=1) * softmax(dim=2) of the dustbin-augmented S/T equals exp(2 s - lse_row - lse_col) with the two
+// log-sum-exps taken over the valid cells plus the dustbin.  Pass 1 (EPI_LSE) emits, from ONE evaluation of the S tile,
+// online-softmax partials (max, sum) of every row over the warp's 64 columns and of every column over the warp's 32
+// rows; a tiny kernel (matcher_lse_reduce_kernel) folds the partials and the dustbin into the two vectors; pass 2
+// (EPI_DUAL) re-evaluates S and writes the outputs.  Everything is kept relative to true row / column maxima, so no
+// logit range (un-normalised descriptors, small temperatures) can underflow a whole row.  All in the log2 domain.
+//
+// Transposing reductions over a warp: lane l holds part[j] = its row's value for column j; after the recursive-halving
+// exchange (31 shuffles) lane j holds the reduction over the 32 rows of column j.  Fixed order, bit-reproducible.
+__device__ __forceinline__ float warp_colmax32(float (&part)[32], int lane) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
-    if (n0 + j < p.n_valid) s += exp2f(fmaf(v[j], k2, -sh));
-  return s;
-}
-
-// Sum of the partial-sum slots of one row, in a fixed order (bit-reproducible), with independent 16-byte loads.
-__device__ __forceinline__ float sum_slots(const float* __restrict__ ptr, int n) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int k = 0;
-  if ((n & 3) == 0) {
-    for (; k < n; k += 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(ptr + k));
-      a0 += t.x; a1 += t.y; a2 += t.z; a3 += t.w;
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = upper ? part[i] : part[i + o];
+      const float keep = upper ? part[i + o] : part[i];
+      part[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
     }
-  } else {
-    for (; k < n; ++k) a0 += __ldg(ptr + k);
   }
-  return (a0 + a1) + (a2 + a3);
+  return part[0];
 }
 
-// EPI_DUAL, coalesced: the warp owns rows row0..row0+31 (lane == row on entry) and columns n0..n0+31.
-// Each lane scales its row by the row statistics (inv_r, s0: computed once per tile by the caller), the 32x32
-// block is transposed through `stage` ([32][33] floats, warp-private), then lane == column applies the column
-// statistics and every store instruction writes one contiguous 128-byte segment of a row of
-// scores / kp_scores / final_scores.
-__device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int row0, int lane, int n0,
-                                                 const float (&v)[32], float* stage, float inv_r, float s0,
-                                                 float sh, float dust) {
-  const float L2E = 1.4426950408889634f;
-  const size_t gv = (size_t)g * p.n_valid;
-  const float k2 = p.inv_temp * L2E;
+#define MK_NEG_INF (__int_as_float(0xff800000))          /* -inf */
+
+// One 32 x 32 chunk of pass 1.  x[j] = S[row][col0 + j] * inv_temp * log2(e), or -inf outside the valid rows / columns.
+// Updates the row's running (rmax, rsum) and stores the column partial of the warp's 32 rows.
+__device__ __forceinline__ void lse_chunk(const GemmParams& p, int g, int col0, int lane, int col_slot, bool row_ok,
+                                          const float (&v)[32], float& rmax, float& rsum) {
+  const float k2 = p.inv_temp * 1.4426950408889634f;
+  float x[32], t[32];
+  float cm = MK_NEG_INF;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const float e = exp2f(fmaf(v[j], k2, -sh));
-    stage[lane * 33 + j] = e * e * inv_r;
+    x[j] = (row_ok && col0 + j < p.n_valid) ? v[j] * k2 : MK_NEG_INF;
+    cm = fmaxf(cm, x[j]);
+    t[j] = x[j];
   }
-  __syncwarp();
+  // rows: online update over the chunks of this warp (a row with no valid cell keeps (-inf, 0))
+  const float nm = fmaxf(rmax, cm);
+  const float base = (nm == MK_NEG_INF) ? 0.f : nm;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc += ex2_approx_f(x[j] - base);
+  rsum = rsum * ex2_approx_f(rmax - base) + acc;
+  rmax = nm;
+  // columns: max over the 32 rows, then the sum relative to it
+  const float cmax_l = warp_colmax32(t, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float cj = __shfl_sync(0xffffffffu, cmax_l, j);
+    t[j] = ex2_approx_f(x[j] - ((cj == MK_NEG_INF) ? 0.f : cj));
+  }
+  const float csum_l = warp_rowsum32(t, lane);
+  const int col = col0 + lane;
+  if (col < p.n_valid) p.part_col[((size_t)g * (p.part_ld / 32) + col_slot) * p.part_ld + col] = make_float2(cmax_l, csum_l);
+}
+
+// Pass 2, one 32 x 32 chunk, coalesced: the warp owns rows row0..row0+31 (lane == row on entry).  Each lane evaluates
+// its row's scores with the column terms read from the warp's staging block (broadcast loads), the block is transposed
+// through `stage` ([32][33] floats + 64 floats of column operands, warp-private), then lane == column writes one
+// contiguous 128-byte row segment per store instruction.  scores / kp_scores may be NULL ("lean" mode).
+__device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int row0, int lane, int n0,
+                                                 const float (&v)[32], float* stage, float lr, float s0) {
+  const float k2x2 = 2.0f * p.inv_temp * 1.4426950408889634f;
+  const size_t gv = (size_t)g * p.n_valid;
   const int col = n0 + lane;
   const bool col_ok = col < p.n_valid;
-  const float inv_c = col_ok ? 1.0f / (sum_slots(p.cs + (gv + col) * p.sum_slots, p.sum_slots) + dust) : 0.0f;
+  float* lcs = stage + 32 * 33;
+  const float lc_l = col_ok ? __ldg(p.lse_c + (size_t)g * p.part_ld + col) : -MK_NEG_INF;     // +inf -> score 0
   const float s1 = col_ok ? __ldg(p.scr1 + gv + col) : 0.0f;
+  lcs[lane] = lc_l;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = ex2_approx_f(fmaf(v[j], k2x2, -lr) - lcs[j]);
+  __syncwarp();
   const int rows = min(32, p.n_valid - row0);
+  const bool full = p.scores != nullptr;
 #pragma unroll 4
   for (int r = 0; r < rows; ++r) {
-    const float sc = stage[r * 33 + lane] * inv_c;
+    const float sc = stage[r * 33 + lane];
     const float kp = __shfl_sync(0xffffffffu, s0, r) * s1;
     if (col_ok) {
       const size_t o = (gv + row0 + r) * (size_t)p.n_valid + col;
-      p.scores[o] = sc;
-      p.kp_scores[o] = kp;
+      if (full) { p.scores[o] = sc; p.kp_scores[o] = kp; }
       p.final_scores[o] = sc * kp;
     }
   }
   __syncwarp();
-}
-
-// per-row quantities of the dual-softmax epilogue for row `my_row` of pair g
-__device__ __forceinline__ void dual_row_setup(const GemmParams& p, int g, int my_row, float& inv_r, float& s0,
-                                               float& sh, float& dust) {
-  const float L2E = 1.4426950408889634f;
-  sh = __ldg(p.shift + g) * L2E;
-  dust = p.dustbin ? exp2f(__ldg(p.dustbin) * L2E - sh) : 0.0f;
-  const size_t gv = (size_t)g * p.n_valid;
-  const bool row_ok = my_row < p.n_valid;
-  inv_r = row_ok ? 1.0f / (sum_slots(p.rs + (gv + my_row) * p.sum_slots, p.sum_slots) + dust) : 0.0f;
-  s0 = row_ok ? __ldg(p.scr0 + gv + my_row) : 0.0f;
 }
 
 // EPI_LN: normalise the 128-wide row (N == 128 == tile width), then optional residual add.

@@ -134,26 +134,8 @@ gemm_simt_kernel(const __half* __restrict__ A, long long a_rows, long long lda, 
       for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
       ln_store_chunk(p, g, m, n0 + c * 32, v, mean, rstd);
     }
-  } else if constexpr (EPI == EPI_LSE) {
-    float s = 0.f;
-    for (int c = 0; c < BN / 32; ++c) {
-      for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
-      s += lse_partial(p, g, n0 + c * 32, v);
-    }
-    if (m < p.n_valid) {
-      float* slot = p.row_sum + ((size_t)g * p.n_valid + m) * p.sum_slots + blockIdx.y * 2;
-      slot[0] = s; slot[1] = 0.f;
-    }
-  } else if constexpr (EPI == EPI_DUAL) {
-    float* stage = reinterpret_cast<float*>(&As[0][0]) + (t >> 5) * (32 * 33);   // tiles are idle now
-    float inv_r, s0, sh, dust;
-    dual_row_setup(p, g, m, inv_r, s0, sh, dust);
-    for (int c = 0; c < BN / 32; ++c) {
-      if (n0 + c * 32 < p.n_valid) {
-        for (int j = 0; j < 32; ++j) v[j] = acc[c * 32 + j];
-        dual_store_chunk(p, g, m0 + (t >> 5) * 32, t & 31, n0 + c * 32, v, stage, inv_r, s0, sh, dust);
-      }
-    }
+  } else if constexpr (EPI == EPI_LSE || EPI == EPI_DUAL) {
+    // the matcher epilogues exist on the tcgen05 kernels only (launch_gemm rejects them for this kernel)
   } else {
     for (int c = 0; c < BN / 32; ++c) {
       if (n0 + c * 32 < p.N) {
@@ -251,10 +233,12 @@ static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorM
   return MK_OK;
 }
 
-// opt-in: cta_group::2 kernel (256 x 256 tiles over a CTA pair), not yet validated on hardware
+// cta_group::2 kernel (256 x 256 tiles over a CTA pair): on by default where every CTA pair gets a tile
+// (MICKEY_GEMM_2SM=0 disables).  First run on B200 in round 2: 16384x4096x4096 1365 -> 1526 TFLOP/s, the 4 x (512->512)
+// 3x3 head convolution 75.8 -> 64.7 us (1055 -> 1238 TFLOP/s) against the 1-SM persistent kernel with 128 x 256 tiles.
 static bool two_sm_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MICKEY_GEMM_2SM"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_2SM"); v = (e && e[0] == '0') ? 0 : 1; }
   return v != 0;
 }
 
@@ -335,7 +319,8 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
       // 128 x 256 tiles (one N=256 UMMA per K step, A tile re-read half as often: 85 instead of 64 flop per byte of
       // L2 traffic, which is what bounds the 128 x 128 tiling) when N allows and enough tiles remain
       if constexpr (BN == 128 && (EPI == EPI_STORE_H || EPI == EPI_RESID_F || EPI == EPI_CONV || EPI == EPI_STORE_F)) {
-        if (two_sm_enabled() && p.N % 256 == 0)      // tmB's 128-row box is exactly one CTA's half of the 256 B rows
+        // tmB's 128-row box is exactly one CTA's half of the 256 B rows
+        if (two_sm_enabled() && p.N % 256 == 0 && (long long)ceil_div(p.M, 256) * (p.N / 256) * grid.z >= sm_count() / 2)
           return launch_2sm<EPI>(dim3(ceil_div(p.M, 256), p.N / 256, grid.z), tmA, tmB, p, stream);
         if (wide_enabled() && p.N % 256 == 0 && (ctas / 2) * 100 >= (long long)wide_min_pct() * sm_count()) {
           CUtensorMap tmB2;
@@ -379,6 +364,8 @@ int launch_gemm(int epi, const GemmOperand& A, const GemmOperand& B, const GemmP
   if (impl == GEMM_IMPL_DEFAULT) impl = use_simt() ? GEMM_IMPL_SIMT : GEMM_IMPL_TC;
   if (p.k_chunks <= 0 || p.M <= 0 || p.N <= 0 || p.groups <= 0) { set_last_error("bad GEMM shape"); return MK_ERR_INVALID; }
   const bool matcher = (epi == EPI_LSE || epi == EPI_DUAL);
+  if (matcher && impl == GEMM_IMPL_SIMT) { set_last_error("the matcher epilogues run on the tcgen05 kernels only"); return MK_ERR_UNSUPPORTED; }
+  if (matcher && (p.part_ld % 128 || p.part_ld < p.n_valid)) { set_last_error("matcher: part_ld must be n_valid rounded up to 128"); return MK_ERR_INVALID; }
   if (!matcher && (p.N % 32)) { set_last_error("GEMM N=%d must be a multiple of 32", p.N); return MK_ERR_INVALID; }
   int bn = (matcher || p.N % 128 == 0) ? 128 : 64;
   if (!matcher && p.N % bn) { set_last_error("GEMM N=%d not tileable", p.N); return MK_ERR_INVALID; }

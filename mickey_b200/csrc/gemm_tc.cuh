@@ -214,22 +214,27 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0
     resid_ln_pass3(p, row0, lane, col_base, stage, mean, rstd);
     cluster_sync_all();                  // no CTA may exit while a peer can still read its statistics
   } else if constexpr (EPI == EPI_LSE) {
-    float s = 0.f;
-    for (int c = c_begin; c < c_end; ++c) {
-      tmem_ld32(taddr + c * 32, v);
-      s += lse_partial(p, g, n0 + c * 32, v);
-    }
-    release();
-    if (m < p.n_valid) p.row_sum[((size_t)g * p.n_valid + m) * p.sum_slots + n_tile * 2 + half] = s;
-  } else if constexpr (EPI == EPI_DUAL) {
-    // 32x33 fp32 staging tile: transposes "thread == row" into "lane == column" so that every store instruction
-    // writes one contiguous 128-byte row segment
-    float inv_r, s0, sh, dust;
-    dual_row_setup(p, g, m, inv_r, s0, sh, dust);
+    static_assert(BN == 128, "matcher epilogues: 128-wide tiles");
+    const bool row_ok = m < p.n_valid;
+    float rmax = MK_NEG_INF, rsum = 0.f;
     for (int c = c_begin; c < c_end; ++c) {
       if (n0 + c * 32 < p.n_valid) {
         tmem_ld32(taddr + c * 32, v);
-        dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage, inv_r, s0, sh, dust);
+        lse_chunk(p, g, n0 + c * 32, lane, (m0 / BLOCK_M) * 4 + q, row_ok, v, rmax, rsum);
+      }
+    }
+    release();
+    if (row_ok) p.part_row[((size_t)g * (p.part_ld / 64) + n_tile * 2 + half) * p.part_ld + m] = make_float2(rmax, rsum);
+  } else if constexpr (EPI == EPI_DUAL) {
+    static_assert(BN == 128, "matcher epilogues: 128-wide tiles");
+    // per-row operands: lse of the row (+inf for rows beyond the valid range -> score 0) and its keypoint score
+    const bool row_ok = m < p.n_valid;
+    const float lr = row_ok ? __ldg(p.lse_r + (size_t)g * p.part_ld + m) : -MK_NEG_INF;
+    const float s0 = row_ok ? __ldg(p.scr0 + (size_t)g * p.n_valid + m) : 0.0f;
+    for (int c = c_begin; c < c_end; ++c) {
+      if (n0 + c * 32 < p.n_valid) {
+        tmem_ld32(taddr + c * 32, v);
+        dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage, lr, s0);
       }
     }
     release();

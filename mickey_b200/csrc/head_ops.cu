@@ -308,36 +308,42 @@ int desc_out(const float* y, float* dsc_cm, void* dsc_x, float* nrm2, int n_img,
   return MK_OK;
 }
 
-// Softmax shift per pair (an upper bound of every logit so that exp never overflows):
-//   shift[b] = max( max_i|d0_i| * max_j|d1_j| / T , dustbin )        (Cauchy-Schwarz)
-// One block per pair.
+// Fold the online-softmax partials of matcher pass 1 (EPI_LSE: float2 (max, sum) per slot, slot-major) and the dustbin
+// logit into the log2-domain log-sum-exp of every row and column of the dustbin-augmented S/T
+// (feature_matcher.py:70-77: the dustbin score is appended AFTER the division by the temperature).
+// grid = (ceil(N / 256), B, 2): z = 0 rows, z = 1 columns.  One thread per row/column; consecutive threads read
+// consecutive float2 of a slot (coalesced); the slots are combined in index order (bit-reproducible).
 __global__ void __launch_bounds__(256)
-matcher_prep_kernel(const float* __restrict__ nrm2, const float* __restrict__ dustbin, float inv_temp,
-                    float* __restrict__ shift, int B, int N) {
+matcher_lse_reduce_kernel(const float2* __restrict__ part_row, const float2* __restrict__ part_col, const float* __restrict__ dustbin,
+                          int N, int part_ld, float* __restrict__ lse_r, float* __restrict__ lse_c) {
   pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
   pdl_trigger();
-  __shared__ float r0[256], r1[256];
-  const int b = blockIdx.x, t = threadIdx.x;
-  float m0 = 0.f, m1 = 0.f;
-  for (int n = t; n < N; n += 256) {
-    m0 = fmaxf(m0, nrm2[(long long)b * N + n]);
-    m1 = fmaxf(m1, nrm2[(long long)(B + b) * N + n]);
+  const int i = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y, which = blockIdx.z;
+  if (i >= N) return;
+  const int slots = which ? part_ld / 32 : part_ld / 64;
+  const float2* src = (which ? part_col : part_row) + (size_t)b * slots * part_ld + i;
+  const float NEG_INF = __int_as_float(0xff800000);
+  float M = dustbin ? __ldg(dustbin) * 1.4426950408889634f : NEG_INF;
+  float S = dustbin ? 1.0f : 0.0f;
+  for (int s0 = 0; s0 < slots; s0 += 8) {
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (s0 + k < slots) ? __ldg(src + (size_t)(s0 + k) * part_ld) : make_float2(NEG_INF, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (v[k].x == NEG_INF) continue;               // a slot without a valid cell
+      const float nm = fmaxf(M, v[k].x);
+      S = S * exp2f(M - nm) + v[k].y * exp2f(v[k].x - nm);
+      M = nm;
+    }
   }
-  r0[t] = m0; r1[t] = m1;
-  __syncthreads();
-  for (int k = 128; k; k >>= 1) {
-    if (t < k) { r0[t] = fmaxf(r0[t], r0[t + k]); r1[t] = fmaxf(r1[t], r1[t + k]); }
-    __syncthreads();
-  }
-  if (t == 0) {
-    float sh = sqrtf(r0[0]) * sqrtf(r1[0]) * inv_temp;
-    if (dustbin) sh = fmaxf(sh, *dustbin);
-    shift[b] = sh;
-  }
+  (which ? lse_c : lse_r)[(size_t)b * part_ld + i] = M + log2f(S);
 }
 
-int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float* shift, int B, int N, cudaStream_t s) {
-  MK_CUDA_CHECK(launch_k(matcher_prep_kernel, dim3(B), dim3(256), 0, s, nrm2, dustbin, inv_temp, shift, B, N));
+int matcher_lse_reduce(const void* part_row, const void* part_col, const float* dustbin, int B, int N, int part_ld, float* lse_r,
+                       float* lse_c, cudaStream_t s) {
+  MK_CUDA_CHECK(launch_k(matcher_lse_reduce_kernel, dim3((N + 255) / 256, B, 2), dim3(256), 0, s, reinterpret_cast<const float2*>(part_row),
+                         reinterpret_cast<const float2*>(part_col), dustbin, N, part_ld, lse_r, lse_c));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }

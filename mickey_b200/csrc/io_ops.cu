@@ -96,7 +96,8 @@ __global__ void pose_to_submission_kernel(const float* __restrict__ pose, int n,
   bool bad = false;
   for (int k = 0; k < 9; ++k) bad |= isnan(p[k]);                       // np.isnan(R).any()          (submission.py:51)
   for (int k = 9; k < 12; ++k) bad |= isnan(p[k]) || isinf(p[k]);       // isnan(t).any() or isinf(t).any()
-  const double Qxx = p[0], Qxy = p[1], Qxz = p[2], Qyx = p[3], Qyy = p[4], Qyz = p[5], Qzx = p[6], Qzy = p[7], Qzz = p[8];
+  // transforms3d names the row-major entries M.flat as Qxx, Qyx, Qzx, Qxy, Qyy, Qzy, Qxz, Qyz, Qzz (quaternions.py mat2quat)
+  const double Qxx = p[0], Qyx = p[1], Qzx = p[2], Qxy = p[3], Qyy = p[4], Qzy = p[5], Qxz = p[6], Qyz = p[7], Qzz = p[8];
   // transforms3d.quaternions.mat2quat: K is symmetric, its principal eigenvector (x, y, z, w) is the quaternion
   double a[4][4], v[4][4];
   a[0][0] = (Qxx - Qyy - Qzz) / 3.0; a[1][1] = (Qyy - Qxx - Qzz) / 3.0; a[2][2] = (Qzz - Qxx - Qyy) / 3.0; a[3][3] = (Qxx + Qyy + Qzz) / 3.0;

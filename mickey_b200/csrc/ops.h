@@ -23,7 +23,8 @@ int kp_head_out(const float* y, const float* w_depth, const float* w_xy, const f
                 float* score_raw, float* scr, int n_img, int gh, int gw, int depth_sigmoid, float max_depth,
                 float down_factor, int use_softmax, cudaStream_t s);
 int desc_out(const float* y, float* dsc_cm, void* dsc_x, float* nrm2, int n_img, int gh, int gw, int normalize, cudaStream_t s);
-int matcher_prep(const float* nrm2, const float* dustbin, float inv_temp, float* shift, int B, int N, cudaStream_t s);
+int matcher_lse_reduce(const void* part_row, const void* part_col, const float* dustbin, int B, int N, int part_ld, float* lse_r,
+                       float* lse_c, cudaStream_t s);
 
 // ransac.cu
 struct RansacParams {

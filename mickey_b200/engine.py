@@ -352,17 +352,18 @@ class Engine:
                       _lib.ptr(dsc), _lib.ptr(ws), ws.numel(), self._stream()), "mk_extract")
         return kps, depth, scr, dsc
 
-    def match(self, B: int, N: int):
+    def match(self, B: int, N: int, lean: bool = False):
+        """lean: only final_scores (the matrix the solver reads) is materialised; scores / kp_scores come back as None."""
         dev = self.device
-        scores = torch.empty(B, N, N, device=dev)
-        kp_scores = torch.empty(B, N, N, device=dev)
+        scores = None if lean else torch.empty(B, N, N, device=dev)
+        kp_scores = None if lean else torch.empty(B, N, N, device=dev)
         final = torch.empty(B, N, N, device=dev)
         _lib.check(self.lib.mk_match(self.h, B, _lib.ptr(scores), _lib.ptr(kp_scores), _lib.ptr(final),
                                      _lib.ptr(self.ws), self.ws.numel(), self._stream()), "mk_match")
         return scores, kp_scores, final
 
     # -- whole path in one C call, optionally replayed from a CUDA graph -------------------------------------------
-    def _static_buffers(self, B, H, W, u8=False):
+    def _static_buffers(self, B, H, W, u8=False, lean=False):
         dev, c = self.device, self.mkcfg
         N = (H // PATCH) * (W // PATCH)
         f = lambda *s: torch.empty(*s, device=dev)                       # noqa: E731
@@ -370,7 +371,8 @@ class Engine:
             "images": torch.empty(2 * B, H, W, 3, dtype=torch.uint8, device=dev) if u8 else f(2 * B, 3, H, W),
             "K0": f(B, 3, 3), "K1": f(B, 3, 3),
             "kps": f(2 * B, 2, N), "depth": f(2 * B, 1, N), "scr": f(2 * B, 1, N), "dsc": f(2 * B, c.desc_dim, N),
-            "scores": f(B, N, N), "kp_scores": f(B, N, N), "final_scores": f(B, N, N), "pose": f(B, 13),
+            "scores": None if lean else f(B, N, N), "kp_scores": None if lean else f(B, N, N),
+            "final_scores": f(B, N, N), "pose": f(B, 13),
             "best_set": torch.empty(B, dtype=torch.int32, device=dev), "inlier_mask": f(B, c.num_sampled),
             "sampled_idx": torch.empty(B * c.it_matches, c.num_sampled, dtype=torch.int32, device=dev),
             "status": torch.zeros(1, dtype=torch.int32, device=dev),
@@ -386,7 +388,7 @@ class Engine:
             _lib.ptr(st["inlier_mask"]), _lib.ptr(st["sampled_idx"]), _lib.ptr(st["status"]), _lib.ptr(ws), ws.numel(),
             self._stream()), "mk_forward")
 
-    def forward(self, image0, image1, K0, K1, seed: int, use_graph: bool = True):
+    def forward(self, image0, image1, K0, K1, seed: int, use_graph: bool = True, lean: bool = False):
         """Whole hot path (extract -> match -> solve) for a batch of pairs.
 
         Returns the dict of STATIC output tensors of this (B, H, W) geometry.  Two buffer sets alternate, so the
@@ -407,12 +409,13 @@ class Engine:
         self._ws_for(B, H, W)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-        slot = self._slot.get((B, H, W, u8), 0)
-        self._slot[(B, H, W, u8)] = slot ^ 1
-        key = (B, H, W, slot, u8)
+        fmt = (bool(u8), bool(lean))
+        slot = self._slot.get((B, H, W, fmt), 0)
+        self._slot[(B, H, W, fmt)] = slot ^ 1
+        key = (B, H, W, slot, fmt)
         ent = self._graphs.get(key)
         if ent is None or ent["ws_ptr"] != self.ws.data_ptr():
-            ent = {"st": self._static_buffers(B, H, W, u8), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(),
+            ent = {"st": self._static_buffers(B, H, W, u8, lean), "graph": None, "launches": 0, "ws_ptr": self.ws.data_ptr(),
                    "calls": 0, "done": None}
             self._graphs[key] = ent
         st = ent["st"]

@@ -204,13 +204,11 @@ def test_attention(T, heads, scale, impl):
     assert rel_err(out, ref) < 2e-3
 
 
-@pytest.mark.skipif(os.environ.get("MICKEY_TEST_EXPERIMENTAL") != "1" or os.environ.get("MICKEY_GEMM_2SM") != "1",
-                    reason="cta_group::2 GEMM: written after the round-1 GPU budget was spent, not yet run on hardware "
-                           "(run with MICKEY_TEST_EXPERIMENTAL=1 MICKEY_GEMM_2SM=1)")
-def test_gemm_2sm_experimental():
-    """With MICKEY_GEMM_2SM=1 every persistent-route GEMM with N % 256 == 0 runs on gemm_tc_2sm_kernel (256 x 256 tiles
-    over a CTA pair)."""
-    for M, N, K in ((20000, 1536, 768), (4100, 512, 1024), (256, 256, 768)):
+@pytest.mark.skipif(os.environ.get("MICKEY_GEMM_2SM") == "0", reason="cta_group::2 GEMM disabled by MICKEY_GEMM_2SM=0")
+def test_gemm_2sm():
+    """Persistent-route GEMMs with N % 256 == 0 and at least one 256 x 256 tile per CTA pair run on gemm_tc_2sm_kernel
+    (cta_group::2 over a CTA pair); the smaller shapes here take the 1-SM kernels."""
+    for M, N, K in ((20000, 1536, 768), (40000, 512, 1024), (256, 256, 768)):
         a, w, bias = _rand(M, K, seed=70).half(), _rand(N, K, scale=0.05, seed=71).half(), _rand(N, scale=0.1, seed=72)
         out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
         gemm("STORE_H", a, w, M, N, K, bias=bias, act=1, out_h=out, out_h_ld=N)
@@ -279,15 +277,12 @@ def test_linear_attention():
         assert rel_err(got, ref) < 2e-3, g
 
 
-@pytest.mark.parametrize("impl,B,N", [("simt", 2, 300), ("tc", 2, 300), ("tc", 1, 1938), ("tc", 3, 1938)])
-def test_matcher_epilogues_vs_dual_softmax(impl, B, N):
-    """LSE x2 + DUAL epilogues on split-fp16 descriptors == softmax(dim1)*softmax(dim2) with dustbin
-    (N = 1938: the full BASELINE size; B = 3 gives 768 tiles -> persistent kernel)."""
-    T = 0.1
-    d0 = F.normalize(_rand(B, N, 128, seed=31), dim=-1)
-    d1 = F.normalize(_rand(B, N, 128, seed=32), dim=-1)
-    s0, s1 = torch.rand(B, N, device=DEV), torch.rand(B, N, device=DEV)
-    dust = torch.tensor([1.0], device=DEV)
+def _matcher(d0, d1, s0, s1, T, dust, lean=False):
+    """The three launches of the matcher through the operator-level ABI: EPI_LSE (row + column partials from one pass
+    over S), mk_op_matcher_reduce, EPI_DUAL."""
+    lib = _lib.load()
+    B, N, _ = d0.shape
+    npad = (N + 127) // 128 * 128
 
     def split(d, role):
         hi = d.half()
@@ -295,22 +290,80 @@ def test_matcher_epilogues_vs_dual_softmax(impl, B, N):
         return torch.cat([hi, lo, hi] if role == 0 else [hi, hi, lo], dim=-1).reshape(B * N, 384).contiguous()
 
     a0, a1 = split(d0, 0), split(d1, 1)
-    shift = torch.full((B,), 10.0, device=DEV)
-    slots = 2 * ((N + 127) // 128)
-    rs, cs = torch.zeros(B, N, slots, device=DEV), torch.zeros(B, N, slots, device=DEV)
-    common = dict(groups=B, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=1 / T, shift=shift, dustbin=dust)
-    gemm("LSE", a0, a1, N, N, 384, impl=impl, row_sum=rs, **common)
-    gemm("LSE", a1, a0, N, N, 384, impl=impl, row_sum=cs, **common)
-    sc, kp, fin = (torch.zeros(B, N, N, device=DEV) for _ in range(3))
-    gemm("DUAL", a0, a1, N, N, 384, impl=impl, rs=rs, cs=cs, scr0=s0, scr1=s1, scores=sc, kp_scores=kp,
-         final_scores=fin, **common)
+    pr = torch.full((B, npad // 64, npad, 2), float("nan"), device=DEV)
+    pc = torch.full((B, npad // 32, npad, 2), float("nan"), device=DEV)
+    lr, lc = torch.full((B, npad), float("nan"), device=DEV), torch.full((B, npad), float("nan"), device=DEV)
+    common = dict(groups=B, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=1 / T, part_ld=npad)
+    gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
+    _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), B, N, npad, _lib.ptr(lr), _lib.ptr(lc), stream()))
+    fin = torch.zeros(B, N, N, device=DEV)
+    if lean:
+        gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, final_scores=fin, **common)
+        return None, None, fin, lr, lc
+    sc, kp = torch.zeros(B, N, N, device=DEV), torch.zeros(B, N, N, device=DEV)
+    gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
+    return sc, kp, fin, lr, lc
+
+
+def _dual_softmax_ref(d0, d1, T, dust):
     S = torch.einsum("bnd,bmd->bnm", d0.double(), d1.double()) / T
-    full = torch.full((B, N + 1, N + 1), 1.0, dtype=torch.float64, device=DEV)
+    if dust is None:
+        return torch.softmax(S, 1) * torch.softmax(S, 2), S
+    B, N, _ = S.shape
+    full = torch.full((B, N + 1, N + 1), float(dust), dtype=torch.float64, device=S.device)
     full[:, :N, :N] = S
-    ref = (torch.softmax(full, 1) * torch.softmax(full, 2))[:, :N, :N]
+    return (torch.softmax(full, 1) * torch.softmax(full, 2))[:, :N, :N], S
+
+
+@pytest.mark.parametrize("B,N", [(2, 300), (1, 1938), (3, 1938), (1, 128), (2, 129)])
+def test_matcher_epilogues_vs_dual_softmax(B, N):
+    """EPI_LSE + reduce + EPI_DUAL on split-fp16 descriptors == softmax(dim1)*softmax(dim2) with dustbin
+    (N = 1938: the full BASELINE size; B = 3 gives 768 tiles -> persistent kernel; 128 / 129: tile-boundary cases)."""
+    T = 0.1
+    d0 = F.normalize(_rand(B, N, 128, seed=31), dim=-1)
+    d1 = F.normalize(_rand(B, N, 128, seed=32), dim=-1)
+    s0, s1 = torch.rand(B, N, device=DEV), torch.rand(B, N, device=DEV)
+    dust = torch.tensor([1.0], device=DEV)
+    sc, kp, fin, lr, lc = _matcher(d0, d1, s0, s1, T, dust)
+    ref, S = _dual_softmax_ref(d0, d1, T, 1.0)
+    # the two log-sum-exp vectors (log2 domain) of the dustbin-augmented logits
+    lse_r = torch.logsumexp(torch.cat([S, torch.full_like(S[:, :, :1], 1.0)], 2), 2) / math.log(2)
+    lse_c = torch.logsumexp(torch.cat([S, torch.full_like(S[:, :1, :], 1.0)], 1), 1) / math.log(2)
+    assert float((lr[:, :N].double() - lse_r).abs().max()) < 1e-4 and float((lc[:, :N].double() - lse_c).abs().max()) < 1e-4
     assert rel_err(sc, ref) < 1e-4
     assert rel_err(kp, s0[:, :, None] * s1[:, None, :]) < 1e-6
     assert rel_err(fin, ref * s0[:, :, None].double() * s1[:, None, :].double()) < 1e-4
+    # lean mode (scores / kp_scores NULL): final_scores is bit-identical
+    _, _, fin2, _, _ = _matcher(d0, d1, s0, s1, T, dust, lean=True)
+    assert torch.equal(fin, fin2)
+
+
+@pytest.mark.parametrize("scale,T,use_dust", [(6.0, 0.1, True), (6.0, 0.1, False), (1.0, 0.01, False), (40.0, 1.0, True)])
+def test_matcher_wide_logit_range(scale, T, use_dust):
+    """Un-normalised descriptors / small temperatures (NORM_DSC: False, TEMPERATURE): logits span thousands, far beyond
+    what one global shift can hold in fp32 (exp underflows below -87).  The reference's softmaxes subtract true row /
+    column maxima (F.softmax); so do the epilogues: every output is finite and matches fp64 wherever it is not negligible."""
+    B, N = 2, 500
+    d0, d1 = _rand(B, N, 128, seed=41) * scale, _rand(B, N, 128, seed=42) * scale
+    d0[0, 7] *= 3.0                                       # one dominant row
+    d1[1, 9] *= 3.0                                       # one dominant column
+    s0, s1 = torch.rand(B, N, device=DEV), torch.rand(B, N, device=DEV)
+    dust = torch.tensor([1.0], device=DEV) if use_dust else None
+    sc, kp, fin, lr, lc = _matcher(d0, d1, s0, s1, T, dust)
+    assert bool(torch.isfinite(sc).all()) and bool(torch.isfinite(fin).all()) and bool(torch.isfinite(lr[:, :N]).all())
+    # split-fp16 operands carry ~2^-22 relative error per product term: compare against the SAME rounded operands in fp64
+    def rounded(d):
+        hi = d.half().double()
+        return hi + (d.double() - hi).half().double()
+    ref, S = _dual_softmax_ref(rounded(d0), rounded(d1), T, 1.0 if use_dust else None)
+    assert float(S.abs().max()) > 500                     # the regime this test is about
+    # absolute error of a logit ~ |s| * 2^-21 -> relative error of exp(2s - ...) ~ 2 * that
+    tol = 4 * float(S.abs().max()) * 2.0 ** -21 + 1e-4
+    big = ref > 1e-6
+    assert float(((sc.double() - ref).abs() / ref.clamp_min(1e-300))[big].max()) < tol
+    assert float((sc.double() - ref).abs().max()) < tol
+    if not use_dust:                                      # without a dustbin every row / column of a softmax sums to <= 1 and the maxima carry mass
+        assert float(sc.sum(-1).max()) <= 1 + 4 * tol and float(sc.max()) > 0.1
 
 
 @pytest.mark.parametrize("M,N,K", [(3878, 384, 384),      # ViT-S attn.proj at 720x540: 31 x 3 tiles, deep ring, clusters of 3

@@ -86,14 +86,26 @@ def split(d, role):
 
 
 a0, a1 = split(d0, 0), split(d1, 1)
-shift, dust = torch.full((1,), 10.0, device=dev), torch.ones(1, device=dev)
-rs, cs = torch.zeros(1, N, 32, device=dev), torch.ones(1, N, 32, device=dev)
+dust = torch.ones(1, device=dev)
+NP = (N + 127) // 128 * 128
+pr, pc = torch.zeros(1, NP // 64, NP, 2, device=dev), torch.zeros(1, NP // 32, NP, 2, device=dev)
+lr, lc = torch.zeros(1, NP, device=dev), torch.zeros(1, NP, device=dev)
 s0, s1 = torch.rand(1, N, device=dev), torch.rand(1, N, device=dev)
 sc, kp, fin = (torch.empty(1, N, N, device=dev) for _ in range(3))
-common = dict(groups=1, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, shift=shift, dustbin=dust)
-report("match.lse", timeit(lambda: gemm("LSE", a0, a1, N, N, 384, row_sum=rs, **common)), 2 * N * N * 384)
-report("match.dual_softmax", timeit(lambda: gemm("DUAL", a0, a1, N, N, 384, rs=rs, cs=cs, scr0=s0, scr1=s1, scores=sc, kp_scores=kp,
-       final_scores=fin, **common)), nbytes=3 * N * N * 4 + 2 * N * 384 * 2)
+common = dict(groups=1, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, part_ld=NP)
+lse = lambda: gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
+red = lambda: _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), 1, N, NP, _lib.ptr(lr), _lib.ptr(lc), stream()))
+dual = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
+dual_lean = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, final_scores=fin, **common)
+lse(); red()
+report("match.lse (rows + columns)", timeit(lse), 2 * N * N * 384)
+report("match.reduce", timeit(red), nbytes=(NP // 64 + NP // 32) * NP * 8)
+report("match.dual_softmax", timeit(dual), nbytes=3 * N * N * 4 + 2 * N * 384 * 2)
+report("match.dual_softmax (lean)", timeit(dual_lean), nbytes=N * N * 4 + 2 * N * 384 * 2)
+report("matcher, all three launches", timeit(lambda: (lse(), red(), dual())), nbytes=3 * N * N * 4 + 2 * N * 128 * 4 + 2 * N * 4)
+wr = torch.empty(32 * 3 * N * N, device=dev)
+report("(torch fill of 32*3*N*N fp32: write-only stream)", timeit(lambda: wr.fill_(1.0), iters=10), nbytes=32 * 3 * N * N * 4)
+del wr
 cp_src, cp_dst = torch.empty(3 * N * N, device=dev), torch.empty(3 * N * N, device=dev)
 report("(torch copy of 3*N*N fp32)", timeit(lambda: cp_dst.copy_(cp_src)), nbytes=2 * 3 * N * N * 4)
 

@@ -57,14 +57,71 @@ if "dual" in which:
         hi = d.half(); lo = (d - hi.float()).half()
         return torch.cat([hi, lo, hi] if role == 0 else [hi, hi, lo], dim=-1).reshape(N, 384).contiguous()
     a0, a1 = split(d0, 0), split(d1, 1)
-    shift, dust = torch.full((1,), 10.0, device=dev), torch.ones(1, device=dev)
-    rs, cs = torch.zeros(1, N, 32, device=dev), torch.ones(1, N, 32, device=dev)
+    dust = torch.ones(1, device=dev)
+    NP = (N + 127) // 128 * 128
+    pr, pc = torch.zeros(1, NP // 64, NP, 2, device=dev), torch.zeros(1, NP // 32, NP, 2, device=dev)
+    lr, lc = torch.zeros(1, NP, device=dev), torch.zeros(1, NP, device=dev)
     s0, s1 = torch.rand(1, N, device=dev), torch.rand(1, N, device=dev)
     sc, kp, fin = (torch.empty(1, N, N, device=dev) for _ in range(3))
-    common = dict(groups=1, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, shift=shift, dustbin=dust)
+    common = dict(groups=1, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, part_ld=NP)
     for _ in range(reps):
-        gemm("LSE", a0, a1, N, N, 384, row_sum=rs, **common)
-        gemm("DUAL", a0, a1, N, N, 384, rs=rs, cs=cs, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
+        gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
+        _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), 1, N, NP, _lib.ptr(lr), _lib.ptr(lc), stream()))
+        gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
+if "dual_b" in which:       # the matcher at batch 8 (2048 tiles -> persistent kernels; 360 MB of outputs: HBM, not L2)
+    Bm = 8
+    d0 = torch.nn.functional.normalize(torch.randn(Bm, N, 128, device=dev), dim=-1)
+    d1 = torch.nn.functional.normalize(torch.randn(Bm, N, 128, device=dev), dim=-1)
+
+    def split_b(d, role):
+        hi = d.half(); lo = (d - hi.float()).half()
+        return torch.cat([hi, lo, hi] if role == 0 else [hi, hi, lo], dim=-1).reshape(Bm * N, 384).contiguous()
+    a0, a1 = split_b(d0, 0), split_b(d1, 1)
+    dust = torch.ones(1, device=dev)
+    NP = (N + 127) // 128 * 128
+    pr, pc = torch.zeros(Bm, NP // 64, NP, 2, device=dev), torch.zeros(Bm, NP // 32, NP, 2, device=dev)
+    lr, lc = torch.zeros(Bm, NP, device=dev), torch.zeros(Bm, NP, device=dev)
+    s0, s1 = torch.rand(Bm, N, device=dev), torch.rand(Bm, N, device=dev)
+    sc, kp, fin = (torch.empty(Bm, N, N, device=dev) for _ in range(3))
+    common = dict(groups=Bm, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, part_ld=NP)
+    for _ in range(reps):
+        gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
+        _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), Bm, N, NP, _lib.ptr(lr), _lib.ptr(lc), stream()))
+        gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
+if "fc1_b" in which or "qkv_b" in which or "fc2_b" in which:    # ViT-B GEMMs of the B=32 workload (half the batch: 32 images)
+    Mb, Db = 32 * T, 768
+    a = torch.randn(Mb, Db, device=dev).half()
+    if "fc1_b" in which:
+        w, b = (torch.randn(4 * Db, Db, device=dev) * 0.02).half(), torch.randn(4 * Db, device=dev)
+        out = torch.empty(Mb, 4 * Db, dtype=torch.float16, device=dev)
+        for _ in range(reps):
+            gemm("STORE_H", a, w, Mb, 4 * Db, Db, bias=b, act=1, out_h=out, out_h_ld=4 * Db)
+    if "qkv_b" in which:
+        w, b = (torch.randn(3 * Db, Db, device=dev) * 0.02).half(), torch.randn(3 * Db, device=dev)
+        out = torch.empty(Mb, 3 * Db, dtype=torch.float16, device=dev)
+        for _ in range(reps):
+            gemm("STORE_H", a, w, Mb, 3 * Db, Db, bias=b, out_h=out, out_h_ld=3 * Db)
+    if "fc2_b" in which:
+        a4 = torch.randn(Mb, 4 * Db, device=dev).half()
+        w, b, g, x = (torch.randn(Db, 4 * Db, device=dev) * 0.02).half(), torch.randn(Db, device=dev), torch.randn(Db, device=dev), torch.randn(Mb, Db, device=dev)
+        for _ in range(reps):
+            gemm("RESID_F", a4, w, Mb, Db, 4 * Db, bias=b, gamma=g, out_f=x, out_f_ld=Db)
+if "conv_b" in which:       # heads resblock1 conv2 at batch: 32 padded 53x40 images
+    h2, w2, G, Cc = 53, 40, 4, 512
+    R = 32 * h2 * w2
+    a = torch.randn(R, G * Cc, device=dev).half()
+    w = (torch.randn(G * Cc, 9 * Cc, device=dev) * 0.01).half()
+    b = torch.randn(G * Cc, device=dev)
+    out = torch.empty(R, G * Cc, dtype=torch.float16, device=dev)
+    taps = [(ky - 1) * w2 + (kx - 1) for ky in range(3) for kx in range(3)]
+    for _ in range(reps):
+        gemm("CONV", a, w, R, Cc, taps=taps, chunks_per_tap=Cc // 64, groups=G, a_col_group_off=Cc, b_row_group_off=Cc,
+             bias=b, bias_group_off=Cc, act=2, pad_h2=h2, pad_w2=w2, out_h=out, out_h_ld=G * Cc, out_h_group_off=Cc)
+if "attention_b" in which:  # ViT-B attention at batch: 32 images x 12 heads
+    qkv = torch.randn(32 * T, 3 * 768, device=dev).half()
+    out = torch.empty(32 * T, 768, dtype=torch.float16, device=dev)
+    for _ in range(reps):
+        _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), 32, T, 768, 12, 0, stream()))
 if "sampler" in which:
     p = torch.rand(1, N * N, device=dev) * 1e-9
     nb = lib.mk_op_sample_workspace_bytes(1, 8)
