@@ -169,8 +169,7 @@ int mk_op_ingest_u8(const unsigned char* img_u8, void* patches_h, int n_img, int
                     const float* cls_pos, int D, void* stream);
 int mk_op_layernorm(const float* x, const float* w, const float* b, void* out_h, int rows, int D, float eps, int mode,
                     int gh, int gw, void* stream);
-/* impl: 0 = default (tcgen05), 1 = tcgen05/TMEM kernel, 2 = mma.sync kernel (cross-check),
- *       3 = tcgen05 ping-pong kernel (experimental, see attention_tc.cu) */
+/* impl: 0 = default (tcgen05), 1 = tcgen05/TMEM kernel, 2 = mma.sync kernel (cross-check) */
 int mk_op_attention(const void* qkv_h, void* out_h, int n_img, int T, int D, int heads, int impl, void* stream);
 /* kv_part_f: scratch [n_img, G, ceil(h2*w2/32), 8, 272] fp32 */
 int mk_op_linattn(const float* qkv_f, float* kv_part_f, float* kv_f, void* msg_h, int n_img, int G, int h2, int w2, float eps,

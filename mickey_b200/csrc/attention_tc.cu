@@ -320,271 +320,19 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   return MK_OK;
 }
 
-// ======================================================================================================
-// Ping-pong variant (opt-in: MICKEY_ATTN_IMPL=pingpong or impl == 3).
-// STATUS: written at the end of round 1 after the GPU budget was spent -- compiles for sm_100a, NOT yet executed on
-// hardware, not used by default, not covered by the default test run.  Rationale (profiles/r01_notes.md): the kernel
-// above keeps the MUFU only 57-64 % busy because the two softmax warps of an SM sub-partition belong to two
-// independent CTAs and their exp phases collide while their ~900-clock non-exp phases leave the MUFU idle.
-//
-// Here one CTA per SM owns TWO 128-query tiles of the same (image, head) and streams K/V once for both:
-//   warps 0-3 : softmax group 0 (Q tile 0), thread == row, lane quadrant = warp & 3
-//   warps 4-7 : softmax group 1 (Q tile 1); warp w + 4 shares the sub-partition (and its MUFU) with warp w
-//   warp 8    : TMA producer (Q0, Q1 once; K and V rings, 3 stages each)
-//   warp 9    : TMEM allocator + single-thread MMA issuer
-// TMEM (all 512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
-// The two softmax warps of a sub-partition hand a "MUFU token" back and forth over a pair of named barriers, so
-// their exp loops strictly alternate: while one exponentiates, the other waits for its S tile, pulls it out of TMEM,
-// takes the row max, stores P and rescales O.  Steady state: 2 x 1071 MUFU clocks per K/V tile and sub-partition
-// instead of the measured 3100-3200.
-constexpr int PP_THREADS = 320, PP_KV_STAGES = 3;
-constexpr int PP_SMEM = FA_TILE_BYTES * (2 + 2 * PP_KV_STAGES) + 1024 + 256;
-constexpr uint32_t PP_COL_S = 0, PP_COL_P = 256, PP_COL_O = 384, PP_TMEM_COLS = 512;
+// A ping-pong variant (one CTA per SM, two Q tiles, the two softmax warps of a sub-partition alternating their exp loops
+// through named barriers) was written at the end of round 1 and measured in round 2: correct, but SLOWER than the kernel
+// above on B200 (one pair: 36.3 vs 31.8 us; 64 images: 1391 vs 1100 us, 7.5 vs 9.5 exp2/clk/SM) -- the strict
+// alternation serialises the two groups' non-exp phases instead of hiding them.  It was removed (profiles/r02_notes.md).
 
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-__global__ void __launch_bounds__(PP_THREADS, 1)
-attention_pp_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int D, float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base;                                         // two tiles
-  const uint32_t sK = base + 2 * FA_TILE_BYTES;
-  const uint32_t sV = sK + PP_KV_STAGES * FA_TILE_BYTES;
-  const uint32_t bars = sV + PP_KV_STAGES * FA_TILE_BYTES;
-  const uint32_t q_full = bars, k_full = bars + 8, k_empty = bars + 32, v_full = bars + 56, v_empty = bars + 80;
-  const uint32_t s_full = bars + 104, s_empty = bars + 120, p_full = bars + 136, pv_done = bars + 152, tmem_slot = bars + 168;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * FA_BQ, head = blockIdx.y, im = blockIdx.z;
-  const int n_tiles = (T + FA_BK - 1) / FA_BK;
-  const int row_base = im * T;
-
-  if (warp == 8 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
-    mbar_init(q_full, 1);
-    for (int s = 0; s < PP_KV_STAGES; ++s) {
-      mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
-      mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
-    }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(s_full + 8 * g, 1); mbar_init(s_empty + 8 * g, 4); mbar_init(p_full + 8 * g, 4); mbar_init(pv_done + 8 * g, 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(PP_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
-  pdl_wait();
-
-  if (warp == 8) {
-    // ===== TMA producer =====
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * FA_TILE_BYTES);
-      tma_load_2d(sQ, &tmQKV, q_full, head * FA_D, row_base + q0);
-      tma_load_2d(sQ + FA_TILE_BYTES, &tmQKV, q_full, head * FA_D, row_base + q0 + FA_BQ);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % PP_KV_STAGES;
-        const uint32_t par = ((j / PP_KV_STAGES) & 1) ^ 1;
-        mbar_wait(k_empty + 8 * st, par);
-        mbar_expect_tx(k_full + 8 * st, FA_TILE_BYTES);
-        tma_load_2d(sK + st * FA_TILE_BYTES, &tmQKV, k_full + 8 * st, D + head * FA_D, row_base + j * FA_BK);
-        mbar_wait(v_empty + 8 * st, par);
-        mbar_expect_tx(v_full + 8 * st, FA_TILE_BYTES);
-        tma_load_2d(sV + st * FA_TILE_BYTES, &tmQKV, v_full + 8 * st, 2 * D + head * FA_D, row_base + j * FA_BK);
-      }
-    }
-  } else if (warp == 9) {
-    // ===== MMA issuer: QK0(j), QK1(j), then PV0(j-1), PV1(j-1) -- the S tiles of step j are in flight while the softmax
-    // groups finish step j-1 =====
-    constexpr uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FA_BK >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
-    constexpr uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
-    auto issue_pv = [&](int i) {
-      const int sv = i % PP_KV_STAGES;
-      mbar_wait(v_full + 8 * sv, (i / PP_KV_STAGES) & 1);
-      for (int g = 0; g < 2; ++g) {
-        mbar_wait(p_full + 8 * g, i & 1);                    // P_g(i) written (and O_g rescaled if needed)
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t dv = umma_desc_mn_sw128(sV + sv * FA_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < FA_BK / UMMA_K; ++k)
-            umma_f16_ts(tmem_base + PP_COL_O + 64 * g, tmem_base + PP_COL_P + 64 * g + k * 8, dv + (uint64_t)(k * 128), idesc_pv,
-                        (i > 0 || k > 0) ? 1u : 0u);
-          umma_commit(pv_done + 8 * g);
-          if (g == 1) umma_commit(v_empty + 8 * sv);
-        }
-        __syncwarp();
-      }
-    };
-    mbar_wait(q_full, 0);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j % PP_KV_STAGES;
-      mbar_wait(k_full + 8 * st, (j / PP_KV_STAGES) & 1);
-      for (int g = 0; g < 2; ++g) {
-        if (j > 0) mbar_wait(s_empty + 8 * g, (j - 1) & 1);  // group g holds S_g(j-1) in registers
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t da = umma_desc_sw128(sQ + g * FA_TILE_BYTES), db = umma_desc_sw128(sK + st * FA_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < FA_D / UMMA_K; ++k)
-            umma_f16(tmem_base + PP_COL_S + 128 * g, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_qk, k > 0 ? 1u : 0u);
-          umma_commit(s_full + 8 * g);
-          if (g == 1) umma_commit(k_empty + 8 * st);
-        }
-        __syncwarp();
-      }
-      if (j > 0) issue_pv(j - 1);
-    }
-    issue_pv(n_tiles - 1);
-  } else {
-    // ===== softmax / correction / epilogue: group g = warp >> 2 owns Q tile g =====
-    const int g = warp >> 2, quad = warp & 3;
-    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + PP_COL_S + 128 * g, tP = tmem_base + lane_off + PP_COL_P + 64 * g;
-    const uint32_t tO = tmem_base + lane_off + PP_COL_O + 64 * g;
-    const uint32_t my_token = 1 + g * 4 + quad, other_token = 1 + (g ^ 1) * 4 + quad;   // named barriers 1..8
-    const uint32_t sfull = s_full + 8 * g, sempty = s_empty + 8 * g, pfull = p_full + 8 * g, pvdone = pv_done + 8 * g;
-    if (g == 1) named_bar_arrive(other_token, 64);       // group 0 exponentiates first
-    float m_ref = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(sfull, j & 1);
-      tc_fence_after();
-      float s[128];
-      {
-        float v[32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld32(tS + c * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = v[i];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sempty);          // S_g may be overwritten by QK^T of the next tile
-      const int valid = T - j * FA_BK;             // keys of this tile that exist (>= 1)
-      if (valid < FA_BK) {                         // only the last tile has a key tail (warp-uniform branch)
-#pragma unroll
-        for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : -INFINITY;
-      }
-      float mxa[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) mxa[k] = s[k];
-#pragma unroll
-      for (int i = 8; i < 128; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[i]);
-      float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-      mx *= scale_log2;
-      float alpha = 1.0f;
-      const bool move = (mx > m_ref + 8.0f);       // always true for j == 0 (m_ref = -inf)
-      if (move) { alpha = ex2_approx(m_ref - mx); m_ref = mx; }
-      const float neg_m = -m_ref;
-      // ---- the MUFU phase: only one of the sub-partition's two softmax warps is in here at a time
-      named_bar_sync(my_token, 64);
-      float sa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float x0 = fmaf(s[2 * i], scale_log2, neg_m), x1 = fmaf(s[2 * i + 1], scale_log2, neg_m);
-        const bool poly = (i & 3) == 3;            // a quarter of the logits on the FMA pipe, as in the kernel above
-        const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
-        sa[(2 * i) & 7] += p0; sa[(2 * i + 1) & 7] += p1;
-        __half2 h = __floats2half2_rn(p0, p1);
-        pk[i] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      if (!(g == 1 && j == n_tiles - 1)) named_bar_arrive(other_token, 64);   // hand the MUFU over (no dangling arrival at exit)
-      const float sum = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
-      l_run = l_run * alpha + sum;
-      if (j > 0) {
-        mbar_wait(pvdone, (j - 1) & 1);            // P_g free, O_g quiescent
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, move)) {       // rescale this warp's 32 rows of O_g (alpha == 1 where unchanged)
-          float o[32];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(tO + c * 32, o);
-            uint32_t ob[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(o[i] * alpha);
-            tmem_st32(tO + c * 32, ob);
-          }
-        }
-      }
-      {
-        uint32_t half_pk[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) half_pk[i] = pk[c * 32 + i];
-          tmem_st32(tP + c * 32, half_pk);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pfull);
-    }
-    // epilogue: O_g / l -> fp16
-    mbar_wait(pvdone, (n_tiles - 1) & 1);
-    tc_fence_after();
-    pdl_trigger();
-    const int q = q0 + g * FA_BQ + quad * 32 + lane;
-    const float inv = 1.0f / l_run;
-    __half* dst = out + ((long long)(row_base + q)) * D + head * FA_D;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float o[32];
-      tmem_ld32(tO + c * 32, o);
-      if (q < T) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] *= inv;
-        store_h32(dst + c * 32, o);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 9) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PP_TMEM_COLS) : "memory");
-  }
-}
-
-int attention_pp(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s) {
-  if (D != heads * FA_D) { set_last_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads); return MK_ERR_UNSUPPORTED; }
-  static unsigned long long attr_mask = 0;
-  if (first_use_on_device(attr_mask)) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));
-  }
-  CUtensorMap tm;
-  int rc = make_tensor_map_f16(&tm, qkv, (long long)n_img * T, 3LL * D, 3LL * D, FA_BQ);
-  if (rc) return rc;
-  dim3 grid(ceil_div(T, 2 * FA_BQ), heads, n_img);
-  const float scale_log2 = 0.125f * 1.4426950408889634f;
-  MK_CUDA_CHECK(launch_k(attention_pp_kernel, grid, dim3(PP_THREADS), (size_t)PP_SMEM, s, tm, (__half*)out, T, D, scale_log2));
-  return MK_OK;
-}
-
-// impl: 0 = default (tcgen05 unless MICKEY_ATTN_IMPL=mma|pingpong), 1 = tcgen05, 2 = mma.sync, 3 = ping-pong (experimental)
+// impl: 0 = default (tcgen05 unless MICKEY_ATTN_IMPL=mma), 1 = tcgen05, 2 = mma.sync
 int attention_dispatch(const void* qkv, void* out, int n_img, int T, int D, int heads, int impl, cudaStream_t s) {
   if (impl == 0) {
     static int def = 0;
-    if (!def) { const char* e = getenv("MICKEY_ATTN_IMPL"); def = (e && strcmp(e, "mma") == 0) ? 2 : (e && strcmp(e, "pingpong") == 0) ? 3 : 1; }
+    if (!def) { const char* e = getenv("MICKEY_ATTN_IMPL"); def = (e && strcmp(e, "mma") == 0) ? 2 : 1; }
     impl = def;
   }
-  if (impl == 3) return attention_pp(qkv, out, n_img, T, D, heads, s);
+  if (impl != 1 && impl != 2) { set_last_error("attention: unknown impl %d", impl); return MK_ERR_INVALID; }
   return impl == 2 ? attention(qkv, out, n_img, T, D, heads, s) : attention_tc(qkv, out, n_img, T, D, heads, s);
 }
 

@@ -221,21 +221,6 @@ def test_gemm_2sm():
     assert rel_err(x, ref) < 1e-5
 
 
-@pytest.mark.skipif(os.environ.get("MICKEY_TEST_EXPERIMENTAL") != "1",
-                    reason="ping-pong attention kernel: written after the round-1 GPU budget was spent, not yet run on hardware")
-@pytest.mark.parametrize("T,heads,scale", [(211, 6, 1.5), (1939, 6, 1.5), (64, 12, 1.5), (300, 6, 6.0), (513, 6, 1.5)])
-def test_attention_pingpong_experimental(T, heads, scale):
-    """impl 3: one CTA per SM, two Q tiles, MUFU token between the two softmax groups (attention_pp_kernel)."""
-    lib = _lib.load()
-    n_img, D = 2, heads * 64
-    qkv = (_rand(n_img * T, 3 * D, seed=26) * scale).half()
-    out = torch.zeros(n_img * T, D, dtype=torch.float16, device=DEV)
-    _lib.check(lib.mk_op_attention(_lib.ptr(qkv), _lib.ptr(out), n_img, T, D, heads, 3, stream()))
-    q, k, v = qkv.float().reshape(n_img, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
-    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(n_img * T, D)
-    assert rel_err(out, ref) < 2e-3
-
-
 def test_patch_gather_and_patch_epilogue():
     lib = _lib.load()
     n_img, H, W, D = 2, 70, 56, 384

@@ -16,7 +16,7 @@ dev = "cuda"
 which = set(sys.argv[1:]) or {"fc1", "proj", "attention", "conv", "dual", "sampler", "linattn"}
 M, D, T, N = 3878, 384, 1939, 1938
 torch.manual_seed(0)
-reps = 2
+reps = int(os.environ.get('NCU_REPS', '2'))
 
 if "fc1" in which:          # ViT-S fc1: [3878,384] x [1536,384]^T + bias + GELU -> fp16
     a, w, b = torch.randn(M, D, device=dev).half(), (torch.randn(4 * D, D, device=dev) * 0.02).half(), torch.randn(4 * D, device=dev)
