@@ -80,12 +80,17 @@ int mk_extract_u8(mk_handle* h, const unsigned char* images_u8_dev, int n_pairs,
  * (compute_correspondences.py:46-50) and `final_scores = scores * kp_scores` (compute_pose.py:23).
  * Uses the descriptors/scores left in the workspace by mk_extract.  Outputs fp32 [n_pairs, N, N];
  * scores_dev AND kp_scores_dev may both be NULL ("lean" mode: only final_scores, the one matrix the solver reads, is
- * materialised: 17 instead of 47 MB per 720x540 pair); the same holds for mk_forward / mk_forward_u8. */
-int mk_match(mk_handle* h, int n_pairs, float* scores_dev, float* kp_scores_dev, float* final_scores_dev,
+ * materialised: 17 instead of 47 MB per 720x540 pair); the same holds for mk_forward / mk_forward_u8.
+ * nn_pitch: row pitch of the three outputs in floats.  N (or 0) = the reference's contiguous [n_pairs, N, N].  A pitch
+ * that is a multiple of 4 (e.g. N rounded up to 32: 1952 for N = 1938) makes every row 16-byte aligned, which lets the
+ * outputs leave through TMA tensor stores as full 128-byte lines; a caller then views the buffers as
+ * [n_pairs, N, nn_pitch][:, :, :N].  N = 1938 itself cannot be described by a tensor map (7752-byte rows). */
+int mk_match(mk_handle* h, int n_pairs, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, long long nn_pitch,
              void* ws_dev, long long ws_bytes, void* stream);
 
 /* ---- stage 3: probabilistic Procrustes RANSAC
  * replaces e2eProbabilisticProcrustesSolver.estimate_pose_vectorized (probabilisticProcrustes.py:183-348).
+ * final_scores_dev fp32 [n_pairs, N, N] with row pitch nn_pitch floats (N or 0 = contiguous).
  * K0/K1 fp32 [n_pairs,3,3].  pose_dev fp32 [n_pairs,13] = R row-major (9) | t (3) | soft inlier count (1).
  * outer_idx_dev int32 [n_pairs*IT_MATCHES, NUM_SAMPLED] / inner_idx_dev int32 [n_pairs*IT_MATCHES*IT_RANSAC, 3]:
  * when non-NULL they replace the two random draws (:231, :251) — the parity tests inject the reference's.
@@ -97,7 +102,7 @@ int mk_match(mk_handle* h, int n_pairs, float* scores_dev, float* kp_scores_dev,
  * sampled_idx_out_dev int32 [n_pairs*IT_MATCHES, NUM_SAMPLED] (the cells that were drawn),
  * hyp_scores_out_dev fp32 [n_pairs, IT_MATCHES*IT_RANSAC].  status_dev int32[1]: bit0 = not enough non-zero
  * cells, bit1 = candidate overflow, bit2 = non-finite hypothesis (bits 0/2 give the reference's zero pose). */
-int mk_solve_pose(mk_handle* h, const float* final_scores_dev, const float* kps_dev, const float* depth_dev,
+int mk_solve_pose(mk_handle* h, const float* final_scores_dev, long long nn_pitch, const float* kps_dev, const float* depth_dev,
                   const float* K0_dev, const float* K1_dev, int n_pairs, int n_kpts, unsigned long long seed,
                   const int* outer_idx_dev, const int* inner_idx_dev, float* pose_dev, int* best_set_dev,
                   float* inlier_mask_dev, int* sampled_idx_out_dev, float* hyp_scores_out_dev, int* status_dev,
@@ -106,15 +111,15 @@ int mk_solve_pose(mk_handle* h, const float* final_scores_dev, const float* kps_
 /* ---- whole path: replaces MickeyRelativePose.forward (compute_pose.py:20-37) ---- */
 int mk_forward(mk_handle* h, const float* images_dev, const float* K0_dev, const float* K1_dev, int n_pairs,
                int img_h, int img_w, unsigned long long seed, float* kps_dev, float* depth_dev, float* scr_dev,
-               float* dsc_dev, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, float* pose_dev,
-               int* best_set_dev, float* inlier_mask_dev, int* sampled_idx_out_dev, int* status_dev, void* ws_dev,
-               long long ws_bytes, void* stream);
+               float* dsc_dev, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, long long nn_pitch,
+               float* pose_dev, int* best_set_dev, float* inlier_mask_dev, int* sampled_idx_out_dev, int* status_dev,
+               void* ws_dev, long long ws_bytes, void* stream);
 
 int mk_forward_u8(mk_handle* h, const unsigned char* images_u8_dev, const float* K0_dev, const float* K1_dev, int n_pairs,
                   int img_h, int img_w, unsigned long long seed, float* kps_dev, float* depth_dev, float* scr_dev,
-                  float* dsc_dev, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, float* pose_dev,
-                  int* best_set_dev, float* inlier_mask_dev, int* sampled_idx_out_dev, int* status_dev, void* ws_dev,
-                  long long ws_bytes, void* stream);
+                  float* dsc_dev, float* scores_dev, float* kp_scores_dev, float* final_scores_dev, long long nn_pitch,
+                  float* pose_dev, int* best_set_dev, float* inlier_mask_dev, int* sampled_idx_out_dev, int* status_dev,
+                  void* ws_dev, long long ws_bytes, void* stream);
 
 /* ---- after the path: submission records (replaces the per-pair loop of submission.py:43-59)
  * pose_dev fp32 [n_pairs,13] as written by mk_forward / mk_solve_pose -> out_dev fp64 [n_pairs, 9] =
@@ -160,6 +165,7 @@ typedef struct mk_gemm_args {
   const float* lse_r; const float* lse_c;          /* DUAL in: log2-domain log-sum-exp per row / column, [groups, part_ld] (mk_op_matcher_reduce) */
   const float* scr0; const float* scr1;
   float* scores; float* kp_scores; float* final_scores;
+  long long out_pitch;     /* DUAL: row pitch of the outputs in floats (0 = n_valid); % 4 == 0 selects the TMA-store path */
 } mk_gemm_args;
 
 int mk_op_gemm(const mk_gemm_args* args, void* stream);
@@ -176,7 +182,7 @@ int mk_op_linattn(const float* qkv_f, float* kv_part_f, float* kv_f, void* msg_h
                   void* stream);
 int mk_op_matcher_reduce(const float* part_row, const float* part_col, const float* dustbin, int B, int N, int part_ld,
                          float* lse_r, float* lse_c, void* stream);
-int mk_op_sample(const float* final_scores, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
+int mk_op_sample(const float* final_scores, int B, int N, long long pitch, int IM, int n_sample, unsigned long long seed, void* ws,
                  long long ws_bytes, int* idx_out, int* status, void* stream);
 long long mk_op_sample_workspace_bytes(int B, int IM);
 

@@ -67,8 +67,15 @@ struct GemmParams {
   // EPI_DUAL in: log2-domain log-sum-exp of every row / column of the dustbin-augmented S/T, [groups, part_ld]
   const float* lse_r; const float* lse_c;
   const float* scr0; const float* scr1; // [groups, n_valid]
-  float* scores; float* kp_scores; float* final_scores;   // [groups, n_valid, n_valid]
+  float* scores; float* kp_scores; float* final_scores;   // [groups, n_valid, out_pitch]; scores / kp_scores may be NULL (lean)
+  long long out_pitch;      // row pitch of the three N x N outputs in floats (n_valid = contiguous, the reference's layout)
+  int out_tma;              // 1: rows are 16-byte aligned (pitch % 4 == 0) -> the outputs leave through TMA tensor stores
 };
+
+// Tensor maps of the matcher's three outputs (scores, kp_scores, final_scores: fp32 [groups][n_valid][n_valid] with row
+// pitch out_pitch, box 32 x 32, 128-byte swizzle on the shared-memory side).  Every GEMM kernel carries the parameter;
+// only EPI_DUAL with out_tma reads it.
+struct OutMaps { CUtensorMap m[3]; };
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

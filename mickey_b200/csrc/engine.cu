@@ -345,8 +345,10 @@ int run_extract(mk_handle* h, const void* images, int img_fmt, int n_pairs, int 
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------------------
-int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores, float* final_scores, Workspace& w,
-              cudaStream_t st) {
+// nn_pitch: row pitch (floats) of the three N x N outputs; N = the reference's contiguous layout.  With a pitch that is a
+// multiple of 4 (16-byte rows) the outputs leave through TMA tensor stores; N = 1938 itself cannot (7752-byte rows).
+int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores, float* final_scores, long long nn_pitch,
+              Workspace& w, cudaStream_t st) {
   const mk_config& c = h->cfg;
   Lookup L{h};
   const float* dust = c.use_dustbin ? L.f("dustbin", 1) : nullptr;
@@ -355,6 +357,10 @@ int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores,
     set_last_error("mk_match: final_scores is required; scores and kp_scores are given together or both NULL (lean mode)");
     return MK_ERR_INVALID;
   }
+  if (nn_pitch <= 0) nn_pitch = N;
+  if (nn_pitch < N) { set_last_error("mk_match: nn_pitch %lld < N %d", nn_pitch, N); return MK_ERR_INVALID; }
+  const bool tma_ok = nn_pitch % 4 == 0 && reinterpret_cast<uintptr_t>(final_scores) % 16 == 0 &&
+                      (!scores || (reinterpret_cast<uintptr_t>(scores) % 16 == 0 && reinterpret_cast<uintptr_t>(kp_scores) % 16 == 0));
   const float inv_t = 1.0f / c.temperature;
   const __half* A0 = w.DSCX;                                   // role-0 descriptors [n_pairs*N, 384]
   const __half* A1 = w.DSCX + (size_t)n_pairs * N * 384;       // role-1 descriptors
@@ -370,25 +376,26 @@ int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores,
     MK_TRY(gemm(h, "match.lse", EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
   MK_KERNEL("match.reduce", matcher_lse_reduce(w.part_row, w.part_col, dust, n_pairs, N, npad, w.lse_r, w.lse_c, st));
   { GemmParams p = mp(); p.lse_r = w.lse_r; p.lse_c = w.lse_c; p.scr0 = w.scr_copy; p.scr1 = w.scr_copy + (size_t)n_pairs * N;
-    p.scores = scores; p.kp_scores = kp_scores; p.final_scores = final_scores;
+    p.scores = scores; p.kp_scores = kp_scores; p.final_scores = final_scores; p.out_pitch = nn_pitch; p.out_tma = tma_ok ? 1 : 0;
     MK_TRY(gemm(h, "match.dual_softmax", EPI_DUAL, A0, rows, 384, A1, rows, 384, p, st)); }
   return MK_OK;
 }
 
 // ---- stage 3 ----------------------------------------------------------------------------------------------
-int run_solve(mk_handle* h, const float* final_scores, const float* kps, const float* depth, const float* K0,
+int run_solve(mk_handle* h, const float* final_scores, long long nn_pitch, const float* kps, const float* depth, const float* K0,
               const float* K1, int n_pairs, int N, unsigned long long seed, const int* outer_idx, const int* inner_idx,
               float* pose, int* best_set, float* inl_mask, int* sampled_out, float* hyp_scores_out, int* status_out,
               Workspace& w, cudaStream_t st) {
   const mk_config& c = h->cfg;
   RansacParams rp{c.it_matches, c.it_ransac, c.num_sampled, c.num_corr, c.num_refine, c.th_inlier, c.th_soft_inlier, h->seed_dev};
+  if (nn_pitch <= 0) nn_pitch = N;
   if (seed != 0) MK_TRY(seed_set(h->seed_dev, seed, st));      // seed == 0: continue the device-side sequence
   MK_CUDA_CHECK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
   const size_t n_idx = (size_t)n_pairs * c.it_matches * c.num_sampled;
   const int* idx = outer_idx;
   if (!idx) {
     { ProfScope ps_(h, "solve.sample_outer", st); h->launches += 4;
-      MK_TRY(sample_outer(final_scores, n_pairs, N, c.it_matches, c.num_sampled, h->seed_dev, w.samp_ws, w.idx, w.status, st)); }
+      MK_TRY(sample_outer(final_scores, n_pairs, N, nn_pitch, c.it_matches, c.num_sampled, h->seed_dev, w.samp_ws, w.idx, w.status, st)); }
     idx = w.idx;
   }
   const float* kps0 = kps;
@@ -397,7 +404,7 @@ int run_solve(mk_handle* h, const float* final_scores, const float* kps, const f
   const float* d1 = depth + (size_t)n_pairs * N;
   int* bs = best_set ? best_set : w.best_hyp;     // scratch when the caller does not want it
   { ProfScope ps_(h, "solve.ransac", st); h->launches += 3;
-    MK_TRY(ransac_solve(final_scores, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.xyw, w.hyp_scores,
+    MK_TRY(ransac_solve(final_scores, nn_pitch, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.xyw, w.hyp_scores,
                         w.hyp_Rt, w.status, pose, bs, inl_mask, best_set ? w.best_hyp : nullptr, st)); }
   MK_TRY(seed_advance(h->seed_dev, st));
   if (sampled_out) MK_CUDA_CHECK(cudaMemcpyAsync(sampled_out, idx, n_idx * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -504,15 +511,15 @@ int mk_extract_u8(mk_handle* h, const unsigned char* images, int n_pairs, int H,
   return run_extract(h, images, 1, n_pairs, H, W, kps, depth, scr, dsc, w, (cudaStream_t)stream);
 }
 
-int mk_match(mk_handle* h, int n_pairs, float* scores, float* kp_scores, float* final_scores, void* ws,
+int mk_match(mk_handle* h, int n_pairs, float* scores, float* kp_scores, float* final_scores, long long nn_pitch, void* ws,
              long long ws_bytes, void* stream) {
   Workspace w;
   MK_TRY(check_ws(h, n_pairs, h ? h->geo_h : 0, h ? h->geo_w : 0, ws, ws_bytes, w));
   const Geo g = make_geo(n_pairs, h->geo_h, h->geo_w);
-  return run_match(h, n_pairs, g.N, scores, kp_scores, final_scores, w, (cudaStream_t)stream);
+  return run_match(h, n_pairs, g.N, scores, kp_scores, final_scores, nn_pitch, w, (cudaStream_t)stream);
 }
 
-int mk_solve_pose(mk_handle* h, const float* final_scores, const float* kps, const float* depth, const float* K0,
+int mk_solve_pose(mk_handle* h, const float* final_scores, long long nn_pitch, const float* kps, const float* depth, const float* K0,
                   const float* K1, int n_pairs, int n_kpts, unsigned long long seed, const int* outer_idx,
                   const int* inner_idx, float* pose, int* best_set, float* inl_mask, int* sampled_out,
                   float* hyp_scores_out, int* status, void* ws, long long ws_bytes, void* stream) {
@@ -520,38 +527,38 @@ int mk_solve_pose(mk_handle* h, const float* final_scores, const float* kps, con
   MK_TRY(check_ws(h, n_pairs, h ? h->geo_h : 0, h ? h->geo_w : 0, ws, ws_bytes, w));
   const Geo g = make_geo(n_pairs, h->geo_h, h->geo_w);
   if (n_kpts != g.N) { set_last_error("n_kpts %d does not match the geometry (%d)", n_kpts, g.N); return MK_ERR_INVALID; }
-  return run_solve(h, final_scores, kps, depth, K0, K1, n_pairs, n_kpts, seed, outer_idx, inner_idx, pose, best_set,
+  return run_solve(h, final_scores, nn_pitch, kps, depth, K0, K1, n_pairs, n_kpts, seed, outer_idx, inner_idx, pose, best_set,
                    inl_mask, sampled_out, hyp_scores_out, status, w, (cudaStream_t)stream);
 }
 
 static int forward_any(mk_handle* h, const void* images, int img_fmt, const float* K0, const float* K1, int n_pairs, int H, int W,
                        unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
-                       float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
-                       int* status, void* ws, long long ws_bytes, void* stream) {
+                       float* kp_scores, float* final_scores, long long nn_pitch, float* pose, int* best_set, float* inl_mask,
+                       int* sampled_out, int* status, void* ws, long long ws_bytes, void* stream) {
   Workspace w;
   MK_TRY(check_ws(h, n_pairs, H, W, ws, ws_bytes, w));
   const Geo g = make_geo(n_pairs, H, W);
   cudaStream_t st = (cudaStream_t)stream;
   MK_TRY(run_extract(h, images, img_fmt, n_pairs, H, W, kps, depth, scr, dsc, w, st));
-  MK_TRY(run_match(h, n_pairs, g.N, scores, kp_scores, final_scores, w, st));
-  return run_solve(h, final_scores, kps, depth, K0, K1, n_pairs, g.N, seed, nullptr, nullptr, pose, best_set, inl_mask,
+  MK_TRY(run_match(h, n_pairs, g.N, scores, kp_scores, final_scores, nn_pitch, w, st));
+  return run_solve(h, final_scores, nn_pitch, kps, depth, K0, K1, n_pairs, g.N, seed, nullptr, nullptr, pose, best_set, inl_mask,
                    sampled_out, nullptr, status, w, st);
 }
 
 int mk_forward(mk_handle* h, const float* images, const float* K0, const float* K1, int n_pairs, int H, int W,
                unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
-               float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
-               int* status, void* ws, long long ws_bytes, void* stream) {
-  return forward_any(h, images, 0, K0, K1, n_pairs, H, W, seed, kps, depth, scr, dsc, scores, kp_scores, final_scores, pose,
-                     best_set, inl_mask, sampled_out, status, ws, ws_bytes, stream);
+               float* kp_scores, float* final_scores, long long nn_pitch, float* pose, int* best_set, float* inl_mask,
+               int* sampled_out, int* status, void* ws, long long ws_bytes, void* stream) {
+  return forward_any(h, images, 0, K0, K1, n_pairs, H, W, seed, kps, depth, scr, dsc, scores, kp_scores, final_scores, nn_pitch,
+                     pose, best_set, inl_mask, sampled_out, status, ws, ws_bytes, stream);
 }
 
 int mk_forward_u8(mk_handle* h, const unsigned char* images, const float* K0, const float* K1, int n_pairs, int H, int W,
                   unsigned long long seed, float* kps, float* depth, float* scr, float* dsc, float* scores,
-                  float* kp_scores, float* final_scores, float* pose, int* best_set, float* inl_mask, int* sampled_out,
-                  int* status, void* ws, long long ws_bytes, void* stream) {
-  return forward_any(h, images, 1, K0, K1, n_pairs, H, W, seed, kps, depth, scr, dsc, scores, kp_scores, final_scores, pose,
-                     best_set, inl_mask, sampled_out, status, ws, ws_bytes, stream);
+                  float* kp_scores, float* final_scores, long long nn_pitch, float* pose, int* best_set, float* inl_mask,
+                  int* sampled_out, int* status, void* ws, long long ws_bytes, void* stream) {
+  return forward_any(h, images, 1, K0, K1, n_pairs, H, W, seed, kps, depth, scr, dsc, scores, kp_scores, final_scores, nn_pitch,
+                     pose, best_set, inl_mask, sampled_out, status, ws, ws_bytes, stream);
 }
 
 int mk_pose_to_submission(const float* pose, int n_pairs, double* out, void* stream) {
@@ -632,6 +639,9 @@ int mk_op_gemm(const mk_gemm_args* a, void* stream) {
   p.eps = a->eps; p.n_valid = a->n_valid; p.inv_temp = a->inv_temp; p.dustbin = a->dustbin;
   p.part_row = reinterpret_cast<float2*>(a->part_row); p.part_col = reinterpret_cast<float2*>(a->part_col); p.part_ld = a->part_ld;
   p.lse_r = a->lse_r; p.lse_c = a->lse_c; p.scr0 = a->scr0; p.scr1 = a->scr1;
+  p.out_pitch = a->out_pitch > 0 ? a->out_pitch : a->n_valid;
+  p.out_tma = (a->final_scores && p.out_pitch % 4 == 0 && reinterpret_cast<uintptr_t>(a->final_scores) % 16 == 0 &&
+               (!a->scores || (reinterpret_cast<uintptr_t>(a->scores) % 16 == 0 && reinterpret_cast<uintptr_t>(a->kp_scores) % 16 == 0))) ? 1 : 0;
   p.scores = a->scores; p.kp_scores = a->kp_scores; p.final_scores = a->final_scores;
   GemmOperand A{a->a, a->a_rows, a->a_cols, a->a_ld}, B{a->b, a->b_rows, a->b_cols, a->b_ld};
   return launch_gemm(a->epi, A, B, p, (cudaStream_t)stream, a->impl);
@@ -662,15 +672,16 @@ int mk_op_matcher_reduce(const float* part_row, const float* part_col, const flo
   return matcher_lse_reduce(part_row, part_col, dustbin, B, N, part_ld, lse_r, lse_c, (cudaStream_t)stream);
 }
 long long mk_op_sample_workspace_bytes(int B, int IM) { return (long long)sampler_workspace_bytes(B, IM) + 512; }
-int mk_op_sample(const float* fs, int B, int N, int IM, int n_sample, unsigned long long seed, void* ws,
+int mk_op_sample(const float* fs, int B, int N, long long pitch, int IM, int n_sample, unsigned long long seed, void* ws,
                  long long ws_bytes, int* idx_out, int* status, void* stream) {
+  if (pitch <= 0) pitch = N;
   if ((long long)sampler_workspace_bytes(B, IM) + 256 > ws_bytes) { set_last_error("sampler workspace too small"); return MK_ERR_INVALID; }
   MK_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), (cudaStream_t)stream));
   // the seed word lives at the (256-byte aligned) end of the caller's workspace
   const size_t off = ((size_t)sampler_workspace_bytes(B, IM) + 255) & ~(size_t)255;
   unsigned long long* sd = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + off);
   MK_TRY(seed_set(sd, seed, (cudaStream_t)stream));
-  return sample_outer(fs, B, N, IM, n_sample, sd, ws, idx_out, status, (cudaStream_t)stream);
+  return sample_outer(fs, B, N, pitch, IM, n_sample, sd, ws, idx_out, status, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -354,6 +354,16 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
   }
 }
 
+// ---- TMA tensor stores (cp.async.bulk.tensor.3d.global.shared::cta) ---------------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- matcher epilogues (reference modules/utils/feature_matcher.py:64-83) -----------------------------------
 // softmax(dim=1) * softmax(dim=2) of the dustbin-augmented S/T equals exp(2 s - lse_row - lse_col) with the two
 // log-sum-exps taken over the valid cells plus the dustbin.  Pass 1 (EPI_LSE) emits, from ONE evaluation of the S tile,
@@ -421,6 +431,7 @@ __device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int
                                                  const float (&v)[32], float* stage, float lr, float s0) {
   const float k2x2 = 2.0f * p.inv_temp * 1.4426950408889634f;
   const size_t gv = (size_t)g * p.n_valid;
+  const size_t go = (size_t)g * p.n_valid * (size_t)p.out_pitch;
   const int col = n0 + lane;
   const bool col_ok = col < p.n_valid;
   float* lcs = stage + 32 * 33;
@@ -438,12 +449,58 @@ __device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int
     const float sc = stage[r * 33 + lane];
     const float kp = __shfl_sync(0xffffffffu, s0, r) * s1;
     if (col_ok) {
-      const size_t o = (gv + row0 + r) * (size_t)p.n_valid + col;
+      const size_t o = go + (size_t)(row0 + r) * (size_t)p.out_pitch + col;
       if (full) { p.scores[o] = sc; p.kp_scores[o] = kp; }
       p.final_scores[o] = sc * kp;
     }
   }
   __syncwarp();
+}
+
+// Pass 2 through TMA: the outputs' rows are 16-byte aligned (row pitch padded to a multiple of 4 floats; the unpadded
+// N = 1938 rows of the reference's contiguous layout are only 8-byte aligned, which no tensor map can describe).
+// thread == row: a lane computes its row's 32 scores, kp_scores and final_scores and writes them as eight 16-byte
+// chunks per output into the warp's three 32 x 32 fp32 staging boxes in the 128-byte-swizzle pattern (chunk k of row r
+// at chunk k ^ (r & 7): conflict-free), then one lane issues three tensor stores (hardware clips rows / columns beyond
+// n_valid).  No transposition pass, full 128-byte lines on the way to L2.
+// `stage`: 3 x 4 KB, 1024-byte aligned, warp-private; `aux`: 64 floats (column operands), warp-private.
+__device__ __forceinline__ void dual_store_chunk_tma(const GemmParams& p, const OutMaps& om, int g, int row0, int lane, int n0,
+                                                     const float (&v)[32], float* stage, float* aux, float lr, float s0) {
+  const float k2x2 = 2.0f * p.inv_temp * 1.4426950408889634f;
+  const size_t gv = (size_t)g * p.n_valid;
+  const int col = n0 + lane;
+  const bool col_ok = col < p.n_valid;
+  const bool full = p.scores != nullptr;
+  // the previous chunk's stores must have finished READING the staging boxes
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  aux[lane] = col_ok ? __ldg(p.lse_c + (size_t)g * p.part_ld + col) : -MK_NEG_INF;
+  aux[32 + lane] = col_ok ? __ldg(p.scr1 + gv + col) : 0.0f;
+  __syncwarp();
+  float4* b_sc = reinterpret_cast<float4*>(stage) + lane * 8;
+  float4* b_kp = b_sc + 256;
+  float4* b_fs = b_sc + 512;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 lc = *reinterpret_cast<const float4*>(aux + 4 * k), s1 = *reinterpret_cast<const float4*>(aux + 32 + 4 * k);
+    float4 sc, kp, fs;
+    sc.x = ex2_approx_f(fmaf(v[4 * k + 0], k2x2, -lr) - lc.x); sc.y = ex2_approx_f(fmaf(v[4 * k + 1], k2x2, -lr) - lc.y);
+    sc.z = ex2_approx_f(fmaf(v[4 * k + 2], k2x2, -lr) - lc.z); sc.w = ex2_approx_f(fmaf(v[4 * k + 3], k2x2, -lr) - lc.w);
+    kp.x = s0 * s1.x; kp.y = s0 * s1.y; kp.z = s0 * s1.z; kp.w = s0 * s1.w;
+    fs.x = sc.x * kp.x; fs.y = sc.y * kp.y; fs.z = sc.z * kp.z; fs.w = sc.w * kp.w;
+    const int kk = k ^ sw;
+    if (full) { b_sc[kk] = sc; b_kp[kk] = kp; }
+    b_fs[kk] = fs;
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage);
+    if (full) { tma_store_3d(&om.m[0], sa, n0, row0, g); tma_store_3d(&om.m[1], sa + 4096, n0, row0, g); }
+    tma_store_3d(&om.m[2], sa + 8192, n0, row0, g);
+    tma_store_commit();
+  }
 }
 
 // EPI_LN: normalise the 128-wide row (N == 128 == tile width), then optional residual add.

@@ -80,6 +80,28 @@ static int encode_tensor_map_f16(CUtensorMap* map, const void* ptr, long long ro
   return MK_OK;
 }
 
+// fp32 [groups][n][n] tensor with row pitch `pitch` floats: box = 32 columns (128 bytes) x 32 rows x 1, 128-byte swizzle
+// on the shared-memory side (the layout dual_store_chunk_tma writes), out-of-range rows / columns clipped by the hardware.
+static int encode_tensor_map_out_f32(CUtensorMap* map, const void* ptr, long long n, long long pitch, long long groups) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MK_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch % 4) || pitch < n) {
+    set_last_error("TMA output needs a 16-byte aligned base and a row pitch that is a multiple of 4 floats (ptr=%p pitch=%lld)", ptr, pitch);
+    return MK_ERR_INVALID;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * (cuuint64_t)n};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (fp32 output) failed with CUresult %d", (int)r); return MK_ERR_CUDA; }
+  return MK_OK;
+}
+
+static const OutMaps& no_out_maps() { static OutMaps z = {}; return z; }
+
 // ---- SIMT debug kernel --------------------------------------------------------------------------------
 // Same operand addressing and the same epilogues as the tcgen05 kernel, computed with plain FFMA.  It is
 // NOT a product path: it exists so that a GPU test can tell a tcgen05/TMA descriptor bug from an epilogue
@@ -167,12 +189,13 @@ static bool use_simt() {
 
 template <int BN, int EPI, int STAGES>
 static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  const OutMaps& om = no_out_maps();
   static unsigned long long attr_mask = 0;
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  MK_CUDA_CHECK(launch_k(gemm_tc_kernel<BN, EPI, STAGES>, grid, dim3(GEMM_THREADS), (size_t)smem, stream, tmA, tmB, p));
+  MK_CUDA_CHECK(launch_k(gemm_tc_kernel<BN, EPI, STAGES>, grid, dim3(GEMM_THREADS), (size_t)smem, stream, tmA, tmB, p, om));
   return MK_OK;
 }
 
@@ -193,7 +216,7 @@ static int launch_tc_cluster(dim3 grid, const CUtensorMap& tmA, const CUtensorMa
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, STAGES>, tmA, tmB, p));
+  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, STAGES>, tmA, tmB, p, no_out_maps()));
   return MK_OK;
 }
 
@@ -219,9 +242,10 @@ static int sm_count() {
 }
 
 template <int BN, int EPI>
-static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream,
+                             const OutMaps& om = no_out_maps()) {
   static unsigned long long attr_mask = 0;
-  constexpr int smem = gemm_persistent_smem_bytes<BN>();
+  constexpr int smem = gemm_persistent_smem_bytes<BN, EPI>();
   if (first_use_on_device(attr_mask)) {
     MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
@@ -229,7 +253,7 @@ static int launch_persistent(dim3 tiles, const CUtensorMap& tmA, const CUtensorM
   const long long total = (long long)tiles.x * tiles.y * tiles.z;
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   MK_CUDA_CHECK(launch_k(gemm_tc_persistent_kernel<BN, EPI>, dim3(grid), dim3(PERSIST_THREADS), (size_t)smem, stream, tmA, tmB, p,
-                         (int)tiles.x, (int)tiles.y));
+                         (int)tiles.x, (int)tiles.y, om));
   return MK_OK;
 }
 
@@ -261,7 +285,7 @@ static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI>, tmA, tmB, p, (int)tiles256.x, (int)tiles256.y));
+  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI>, tmA, tmB, p, (int)tiles256.x, (int)tiles256.y, no_out_maps()));
   return MK_OK;
 }
 
@@ -294,6 +318,17 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
     if (rc) return rc;
     rc = make_tensor_map_f16(&tmB, B.ptr, B.rows, B.cols, B.ld, BN);
     if (rc) return rc;
+    if constexpr (EPI == EPI_DUAL) {
+      if (p.out_tma) {
+        // the three N x N outputs leave through TMA tensor stores: always the persistent kernel (its staging area holds
+        // the eight warps' 32 x 32 output boxes; one CTA per SM walks the tile list)
+        OutMaps om = {};
+        float* outs[3] = {p.scores, p.kp_scores, p.final_scores};
+        for (int i = 0; i < 3; ++i)
+          if (outs[i]) { rc = encode_tensor_map_out_f32(&om.m[i], outs[i], p.n_valid, p.out_pitch, p.groups); if (rc) return rc; }
+        return launch_persistent<BN, EPI>(grid, tmA, tmB, p, stream, om);
+      }
+    }
     // grids that give every SM at most ~one CTA run the deep ring; bigger grids keep two CTAs per SM
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     const bool deep = ctas <= (long long)sm_count() * 5 / 4 && p.k_chunks > 3;
@@ -366,6 +401,7 @@ int launch_gemm(int epi, const GemmOperand& A, const GemmOperand& B, const GemmP
   const bool matcher = (epi == EPI_LSE || epi == EPI_DUAL);
   if (matcher && impl == GEMM_IMPL_SIMT) { set_last_error("the matcher epilogues run on the tcgen05 kernels only"); return MK_ERR_UNSUPPORTED; }
   if (matcher && (p.part_ld % 128 || p.part_ld < p.n_valid)) { set_last_error("matcher: part_ld must be n_valid rounded up to 128"); return MK_ERR_INVALID; }
+  if (epi == EPI_DUAL && p.out_pitch < p.n_valid) { set_last_error("matcher: out_pitch %lld < n_valid %d", p.out_pitch, p.n_valid); return MK_ERR_INVALID; }
   if (!matcher && (p.N % 32)) { set_last_error("GEMM N=%d must be a multiple of 32", p.N); return MK_ERR_INVALID; }
   int bn = (matcher || p.N % 128 == 0) ? 128 : 64;
   if (!matcher && p.N % bn) { set_last_error("GEMM N=%d not tileable", p.N); return MK_ERR_INVALID; }

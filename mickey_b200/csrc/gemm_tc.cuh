@@ -33,6 +33,8 @@ template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
   // the ring is reused as the epilogue's staging area (8 warps x 32 rows x (BN/2 + 4) floats), which a 2-stage ring
   // does not cover
+  // (EPI_DUAL's TMA path stages 8 x 12 KB of output boxes + 2 KB of column operands there: 98 KB <= the 3-stage ring of 96 KB + slack is
+  // NOT enough, so the matcher runs on the >= 4-stage instantiations or the persistent kernel: see launch_one)
   constexpr int ring = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2), staging = 8 * 32 * (BN / 2 + 4) * 4;
   // + row statistics of EPI_RESID_LN (never run on the 2-stage ring, whose three CTAs per SM have no room to spare)
   return (ring > staging ? ring : staging) + 1024 /*align slack*/ + 256 /*barriers*/ + (STAGES == 2 ? 0 : 2048);
@@ -145,10 +147,15 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t
 // 32-column chunks (warps q and q+4 split the columns).  `stage` is the warp's private 32 x (BN/2 + 4) fp32
 // staging block; `release()` is called as soon as the accumulator has been read for the last time (the persistent
 // kernel hands the TMEM buffer back to the MMA warp there, before the global stores).
+// Per-warp staging of EPI_DUAL's TMA path: three 32 x 32 fp32 boxes (1024-byte aligned) + 64 floats of column operands
+constexpr int DUAL_STAGE_BYTES = 3 * 4096;
+constexpr int DUAL_AUX_BYTES = 8 * 64 * 4;
+
 template <int BN, int EPI, typename Release>
-__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0, int n0, int n_tile, int q, int half,
+__device__ __forceinline__ void tile_epilogue(const GemmParams& p, const OutMaps& om, int g, int m0, int n0, int n_tile, int q, int half,
                                               int lane, uint32_t tmem_acc, float* stage, Release release,
-                                              float* red = nullptr, uint32_t red_saddr = 0) {
+                                              float* red = nullptr, uint32_t red_saddr = 0, float* dual_stage = nullptr,
+                                              float* dual_aux = nullptr) {
   constexpr int CHUNKS = BN / 32;
   constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
   constexpr int W = BN / 2;                      // columns owned by this warp
@@ -231,10 +238,19 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0
     const bool row_ok = m < p.n_valid;
     const float lr = row_ok ? __ldg(p.lse_r + (size_t)g * p.part_ld + m) : -MK_NEG_INF;
     const float s0 = row_ok ? __ldg(p.scr0 + (size_t)g * p.n_valid + m) : 0.0f;
-    for (int c = c_begin; c < c_end; ++c) {
-      if (n0 + c * 32 < p.n_valid) {
-        tmem_ld32(taddr + c * 32, v);
-        dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage, lr, s0);
+    if (p.out_tma) {
+      for (int c = c_begin; c < c_end; ++c) {
+        if (n0 + c * 32 < p.n_valid && m0 + q * 32 < p.n_valid) {
+          tmem_ld32(taddr + c * 32, v);
+          dual_store_chunk_tma(p, om, g, m0 + q * 32, lane, n0 + c * 32, v, dual_stage, dual_aux, lr, s0);
+        }
+      }
+    } else {
+      for (int c = c_begin; c < c_end; ++c) {
+        if (n0 + c * 32 < p.n_valid) {
+          tmem_ld32(taddr + c * 32, v);
+          dual_store_chunk(p, g, m0 + q * 32, lane, n0 + c * 32, v, stage, lr, s0);
+        }
       }
     }
     release();
@@ -261,7 +277,8 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int g, int m0
 // ---- kernel ------------------------------------------------------------------------------------------
 template <int BN, int EPI, int GEMM_STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, (GEMM_STAGES <= 2) ? 3 : (GEMM_STAGES <= 3) ? 2 : 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+               const __grid_constant__ OutMaps om) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BN * BLOCK_K * 2;
@@ -357,9 +374,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
   pdl_trigger();                 // main loop done: the next kernel's CTAs may start their prologue under our epilogue
-  tile_epilogue<BN, EPI>(p, g, m0, n0, (int)blockIdx.y, warp & 3, warp >> 2, lane, tmem_base,
+  // EPI_DUAL / TMA: the (idle) ring holds the warps' output boxes (1024-byte aligned), the column operands follow them
+  tile_epilogue<BN, EPI>(p, om, g, m0, n0, (int)blockIdx.y, warp & 3, warp >> 2, lane, tmem_base,
                          reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * (BN / 2 + 4)), [] {},
-                         reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)), bar_base + 256);
+                         reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)), bar_base + 256,
+                         reinterpret_cast<float*>(smem_raw + (base - raw) + warp * DUAL_STAGE_BYTES),
+                         reinterpret_cast<float*>(smem_raw + (base - raw) + 8 * DUAL_STAGE_BYTES) + warp * 64);
+  if constexpr (EPI == EPI_DUAL) { if (p.out_tma && lane == 0) tma_store_wait_all(); }   // smem must outlive the bulk reads
 
   tc_fence_before();
   __syncthreads();
@@ -375,29 +396,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // double-buffered in TMEM (2 x BN columns) so that the MMA of tile i+1 runs under the epilogue of tile i:
 //   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warp 3: idle | warps 4-11: epilogue
 constexpr int PERSIST_THREADS = 384;
-template <int BN> constexpr int persist_stages() { return BN >= 256 ? 3 : 4; }      // 3 x 48 KB or 4 x 32 KB
+// 3 x 48 KB or 4 x 32 KB; EPI_DUAL: 3 x 32 KB (K = 384 is six chunks) to make room for the TMA staging boxes
+template <int BN, int EPI = EPI_STORE_H> constexpr int persist_stages() { return (BN >= 256 || EPI == EPI_DUAL) ? 3 : 4; }
 template <int BN> constexpr int staged_cols() { return (BN / 2 > 64) ? 64 : BN / 2; }
+template <int BN, int EPI = EPI_STORE_H> constexpr int persist_staging_bytes() {
+  return (EPI == EPI_DUAL) ? 8 * DUAL_STAGE_BYTES + DUAL_AUX_BYTES : 8 * 32 * (staged_cols<BN>() + 4) * 4;
+}
 
-template <int BN>
+template <int BN, int EPI = EPI_STORE_H>
 constexpr int gemm_persistent_smem_bytes() {
-  return persist_stages<BN>() * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 8 * 32 * (staged_cols<BN>() + 4) * 4 + 1024 + 256;
+  return persist_stages<BN, EPI>() * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + persist_staging_bytes<BN, EPI>() + 1024 + 256;
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const GemmParams p, const int tiles_m, const int tiles_n) {
+                          const GemmParams p, const int tiles_m, const int tiles_n, const __grid_constant__ OutMaps om) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int PERSIST_STAGES = persist_stages<BN>();
-  constexpr int STAGING_BYTES = 8 * 32 * (staged_cols<BN>() + 4) * 4;
+  constexpr int PERSIST_STAGES = persist_stages<BN, EPI>();
+  constexpr int STAGING_BYTES = persist_staging_bytes<BN, EPI>();
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t staging = base + PERSIST_STAGES * STAGE_BYTES;
+  const uint32_t staging = base + PERSIST_STAGES * STAGE_BYTES;        // 1024-byte aligned (stages are 32 / 48 KB)
   const uint32_t bar_base = staging + STAGING_BYTES;
   const uint32_t full_bar0 = bar_base;
   const uint32_t empty_bar0 = bar_base + 8 * PERSIST_STAGES;
@@ -487,6 +512,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int ew = warp - 4;
     const int q = warp & 3, half = ew >> 2;
     float* stage_buf = reinterpret_cast<float*>(smem_raw + (staging - raw)) + ew * (32 * (staged_cols<BN>() + 4));
+    float* dual_stage = reinterpret_cast<float*>(smem_raw + (staging - raw) + ew * DUAL_STAGE_BYTES);
+    float* dual_aux = reinterpret_cast<float*>(smem_raw + (staging - raw) + 8 * DUAL_STAGE_BYTES) + ew * 64;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int g = t / tiles_per_group, r = t - g * tiles_per_group;
@@ -496,13 +523,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_wait(tfull_bar0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tb = tempty_bar0 + 8 * acc;
-      tile_epilogue<BN, EPI>(p, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
+      tile_epilogue<BN, EPI>(p, om, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
-      });
+      }, nullptr, 0, dual_stage, dual_aux);
       __syncwarp();                       // staging block is reused by the next tile
     }
+    if constexpr (EPI == EPI_DUAL) { if (p.out_tma && lane == 0) tma_store_wait_all(); }   // smem must outlive the bulk reads
   }
 
   tc_fence_before();
@@ -564,7 +592,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 template <int EPI>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const GemmParams p, const int tiles_m, const int tiles_n) {
+                   const GemmParams p, const int tiles_m, const int tiles_n, const __grid_constant__ OutMaps om) {
   // tiles_m = ceil(M / 256), tiles_n = N / 256; cluster c = blockIdx.x / 2 walks tiles c, c + gridDim.x / 2, ...
   extern __shared__ uint8_t smem_raw[];
   constexpr int BN = 256;
@@ -677,7 +705,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(tfull_bar0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tb = tempty_bar0 + 8 * acc;
-      tile_epilogue<BN, EPI>(p, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
+      tile_epilogue<BN, EPI>(p, om, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tb, 0);                   // the leader's barrier (also from the leader itself)

@@ -35,9 +35,10 @@ struct RansacParams {
 int seed_set(unsigned long long* s, unsigned long long v, cudaStream_t st);
 int seed_advance(unsigned long long* s, cudaStream_t st);
 size_t sampler_workspace_bytes(int B, int IM);
-int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, const unsigned long long* seed, void* ws,
-                 int* idx_out, int* status, cudaStream_t st);
-int ransac_solve(const float* final_scores, const float* kps0, const float* d0, const float* kps1, const float* d1,
+// final_scores: [B][N][N] with row pitch `pitch` floats (N = contiguous)
+int sample_outer(const float* final_scores, int B, int N, long long pitch, int IM, int n_sample, const unsigned long long* seed,
+                 void* ws, int* idx_out, int* status, cudaStream_t st);
+int ransac_solve(const float* final_scores, long long pitch, const float* kps0, const float* d0, const float* kps1, const float* d1,
                  const float* K0, const float* K1, int B, int N, const RansacParams& rp, const int* outer_idx,
                  const int* inner_idx, float* xyw, float* hyp_scores, float* hyp_Rt, int* status, float* pose,
                  int* best_set, float* inl_mask, int* best_hyp, cudaStream_t st);

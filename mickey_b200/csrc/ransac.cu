@@ -52,40 +52,88 @@ constexpr int SAMP_ELEMS_PER_BLOCK = 256 * 16;
 constexpr uint32_t PHILOX_TAG_PREFIX = 0x5bd1e995u, PHILOX_TAG_LOW = 0x2545F491u;
 
 // ---- pass A: histogram of the cell probabilities of one pair (no random numbers; shared by all its streams) -------
-// A block covers SAMP_ELEMS_PER_BLOCK consecutive cells.  With VEC (N*N a multiple of 4, so every pair's row of cells
-// is 16-byte aligned) a thread issues its four float4 loads before touching any of them: with one scalar load in
+// A block covers SAMP_ELEMS_PER_BLOCK consecutive cells (or 4-cell slots).  final_scores is [N, N] per pair with row
+// pitch `pitch` floats; the logical cell index e = i * N + j (what the generator's counters and the outputs use) does
+// not depend on the pitch.  Addressing modes:
+//   MODE_FLAT_VEC  contiguous rows (pitch == N) with N*N a multiple of 4: 16-byte loads over the flat array
+//   MODE_ROW_VEC   padded rows (pitch % 4 == 0, as the matcher's TMA path writes them): 16-byte loads of 4-cell slots
+//                  per row, slots beyond column N masked
+//   MODE_SCALAR    anything else
+// With the vector modes a thread issues its four float4 loads before touching any of them: with one scalar load in
 // flight per thread these passes were latency-bound at ~1.5 TB/s out of L2.
-template <bool VEC, typename F>
-__device__ __forceinline__ void for_each_cell(const float* __restrict__ p, long long cells, long long chunk, F&& f) {
+enum { MODE_SCALAR = 0, MODE_FLAT_VEC = 1, MODE_ROW_VEC = 2 };
+
+struct CellView {
+  const float* p;          // pair base
+  int N;
+  long long pitch;
+  __device__ __forceinline__ long long cells() const { return (long long)N * N; }
+  __device__ __forceinline__ long long work_items(int mode) const {       // what a block chunk is counted in
+    return mode == MODE_ROW_VEC ? (long long)N * ((N + 3) / 4) * 4 : cells();
+  }
+};
+
+template <int MODE, typename F>
+__device__ __forceinline__ void for_each_cell(const CellView& cv, long long chunk, F&& f) {
   const long long e0 = chunk * SAMP_ELEMS_PER_BLOCK;
-  if (VEC) {
+  if (MODE == MODE_FLAT_VEC) {
+    const long long cells = cv.cells();
     float4 v[4];
     long long e[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       e[i] = e0 + 4LL * (threadIdx.x + SAMP_THREADS * i);
-      v[i] = (e[i] < cells) ? __ldg(reinterpret_cast<const float4*>(p + e[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = (e[i] < cells) ? __ldg(reinterpret_cast<const float4*>(cv.p + e[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       f(e[i], v[i].x); f(e[i] + 1, v[i].y); f(e[i] + 2, v[i].z); f(e[i] + 3, v[i].w);
     }
+  } else if (MODE == MODE_ROW_VEC) {
+    const int spr = (cv.N + 3) / 4;                                  // 4-cell slots per row
+    const long long slots = (long long)cv.N * spr;
+    float4 v[4];
+    long long e[4];
+    int rem[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long sidx = e0 / 4 + threadIdx.x + SAMP_THREADS * i;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f); e[i] = 0; rem[i] = 0;
+      if (sidx < slots) {
+        const int row = (int)(sidx / spr), c4 = (int)(sidx - (long long)row * spr) * 4;
+        v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + (long long)row * cv.pitch + c4));
+        e[i] = (long long)row * cv.N + c4;
+        rem[i] = cv.N - c4;                                          // valid cells in this slot (>= 4 except at the row end)
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (rem[i] > 0) f(e[i], v[i].x);
+      if (rem[i] > 1) f(e[i] + 1, v[i].y);
+      if (rem[i] > 2) f(e[i] + 2, v[i].z);
+      if (rem[i] > 3) f(e[i] + 3, v[i].w);
+    }
   } else {
+    const long long cells = cv.cells();
     const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
-    for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) f(e, p[e]);
+    for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) {
+      const int row = (int)(e / cv.N);
+      f(e, cv.p[(long long)row * cv.pitch + (e - (long long)row * cv.N)]);
+    }
   }
 }
 
-template <bool VEC>
+template <int MODE>
 __global__ void __launch_bounds__(SAMP_THREADS)
-sampler_phist_kernel(const float* __restrict__ fs, long long cells, unsigned int* __restrict__ hist) {
+sampler_phist_kernel(const float* __restrict__ fs, int N, long long pitch, unsigned int* __restrict__ hist) {
   __shared__ unsigned int h[HBINS];
   for (int i = threadIdx.x; i < HBINS; i += SAMP_THREADS) h[i] = 0;
   __syncthreads();
   const int b = blockIdx.y;
-  const long long n_chunks = (cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
+  const CellView cv{fs + (long long)b * N * pitch, N, pitch};
+  const long long n_chunks = (cv.work_items(MODE) + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)      // grid = whole waves of resident blocks
-    for_each_cell<VEC>(fs + (long long)b * cells, cells, chunk, [&](long long, float pv) {
+    for_each_cell<MODE>(cv, chunk, [&](long long, float pv) {
       if (pv > 0.f) atomicAdd(&h[__float_as_uint(pv) >> 20], 1u);
     });
   __syncthreads();
@@ -204,9 +252,9 @@ __device__ __noinline__ void collect_refine(const Philox& rng, long long e, floa
   }
 }
 
-template <bool VEC>
+template <int MODE>
 __global__ void __launch_bounds__(SAMP_THREADS)
-sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, const unsigned long long* __restrict__ seed_ptr,
+sampler_collect_kernel(const float* __restrict__ fs, int N, long long pitch, int IM, const unsigned long long* __restrict__ seed_ptr,
                        const int* __restrict__ thr, const float* __restrict__ inv_tau_p, unsigned long long* __restrict__ cand,
                        unsigned int* __restrict__ cnt, int cap) {
   pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
@@ -215,7 +263,7 @@ sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, co
   const Philox rng(*seed_ptr);
   const int T = thr[b];
   const float inv_tau = inv_tau_p[b];
-  const float* p = fs + (long long)b * cells;
+  const CellView cv{fs + (long long)b * N * pitch, N, pitch};
   auto cell = [&](long long e, float pv) {
     if (!(pv > 0.f)) return;
     // u <= (1 - exp(-y)) * (1 + 2^-10) + 2^-30 with y = p / tau: a superset of the exact condition.  For small y
@@ -234,27 +282,42 @@ sampler_collect_kernel(const float* __restrict__ fs, long long cells, int IM, co
       if (any) collect_refine(rng, e, pv, uth, pth, r, sg, b, IM, T, cand, cnt, cap);
     }
   };
-  const long long n_chunks = (cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
+  const long long n_chunks = (cv.work_items(MODE) + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {    // grid = whole waves of resident blocks
-    const long long e0 = chunk * SAMP_ELEMS_PER_BLOCK;
-    if (VEC) {
+    if (MODE != MODE_SCALAR) {
+      // the four 16-byte loads first, then component-major processing: the loop body holds four (not sixteen)
+      // copies of cell()
+      const long long e0 = chunk * SAMP_ELEMS_PER_BLOCK;
+      const int spr = (N + 3) / 4;
+      const long long cells = cv.cells(), slots = (long long)N * spr;
       float4 v[4];
+      long long eb[4];
+      int rem[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const long long e = e0 + 4LL * (threadIdx.x + SAMP_THREADS * i);
-        v[i] = (e < cells) ? __ldg(reinterpret_cast<const float4*>(p + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f); eb[i] = 0; rem[i] = 0;
+        if (MODE == MODE_FLAT_VEC) {
+          const long long e = e0 + 4LL * (threadIdx.x + SAMP_THREADS * i);
+          if (e < cells) { v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + e)); eb[i] = e; rem[i] = 4; }
+        } else {
+          const long long sidx = e0 / 4 + threadIdx.x + SAMP_THREADS * i;
+          if (sidx < slots) {
+            const int row = (int)(sidx / spr), c4 = (int)(sidx - (long long)row * spr) * 4;
+            v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + (long long)row * pitch + c4));
+            eb[i] = (long long)row * N + c4; rem[i] = N - c4;
+          }
+        }
       }
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {        // component-major: the loop body holds four (not sixteen) copies of cell()
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float pv = (c == 0) ? v[i].x : (c == 1) ? v[i].y : (c == 2) ? v[i].z : v[i].w;
-          cell(e0 + 4LL * (threadIdx.x + SAMP_THREADS * i) + c, pv);
+          if (rem[i] > c) cell(eb[i] + c, pv);
         }
       }
     } else {
-      const long long e1 = min(cells, e0 + SAMP_ELEMS_PER_BLOCK);
-      for (long long e = e0 + threadIdx.x; e < e1; e += SAMP_THREADS) cell(e, p[e]);
+      for_each_cell<MODE_SCALAR>(cv, chunk, cell);
     }
   }
 }
@@ -409,8 +472,8 @@ size_t sampler_workspace_bytes(int B, int IM) {
   return (size_t)B * HBINS * 4 + streams * 4 /*cnt*/ + (size_t)B * 8 /*thr, inv_tau*/ + streams * CAND_CAP * 8 + 512;
 }
 
-int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, const unsigned long long* seed, void* ws,
-                 int* idx_out, int* status, cudaStream_t st) {
+int sample_outer(const float* final_scores, int B, int N, long long pitch, int IM, int n_sample, const unsigned long long* seed,
+                 void* ws, int* idx_out, int* status, cudaStream_t st) {
   if (n_sample > CAND_CAP / 2) { set_last_error("NUM_SAMPLED_MATCHES %d too large", n_sample); return MK_ERR_UNSUPPORTED; }
   const long long cells = (long long)N * N;
   const size_t streams = (size_t)B * IM;
@@ -424,15 +487,19 @@ int sample_outer(const float* final_scores, int B, int N, int IM, int n_sample, 
   MK_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)B * HBINS * 4 + streams * 4, st));
   // one block per 4096-cell chunk (the hardware block scheduler balances the 1.5 waves at chunk granularity); the
   // kernels loop over chunks so that a smaller grid stays correct
-  dim3 grid((unsigned)min((cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK, 65535LL * 16), B);
-  const bool vec = (cells % 4 == 0) && (reinterpret_cast<uintptr_t>(final_scores) % 16 == 0);
-  if (vec) sampler_phist_kernel<true><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
-  else sampler_phist_kernel<false><<<grid, SAMP_THREADS, 0, st>>>(final_scores, cells, hist);
+  const bool aligned = reinterpret_cast<uintptr_t>(final_scores) % 16 == 0;
+  const int mode = (pitch == N && cells % 4 == 0 && aligned) ? MODE_FLAT_VEC : (pitch % 4 == 0 && aligned) ? MODE_ROW_VEC : MODE_SCALAR;
+  const long long items = (mode == MODE_ROW_VEC) ? (long long)N * ((N + 3) / 4) * 4 : cells;
+  dim3 grid((unsigned)min((items + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK, 65535LL * 16), B);
+  if (mode == MODE_FLAT_VEC) sampler_phist_kernel<MODE_FLAT_VEC><<<grid, SAMP_THREADS, 0, st>>>(final_scores, N, pitch, hist);
+  else if (mode == MODE_ROW_VEC) sampler_phist_kernel<MODE_ROW_VEC><<<grid, SAMP_THREADS, 0, st>>>(final_scores, N, pitch, hist);
+  else sampler_phist_kernel<MODE_SCALAR><<<grid, SAMP_THREADS, 0, st>>>(final_scores, N, pitch, hist);
   MK_CUDA_CHECK(cudaGetLastError());
   MK_CUDA_CHECK(launch_k(sampler_tau_kernel, dim3(B), dim3(TAU_THREADS), 0, st, hist, n_sample, thr, inv_tau, status));
   MK_CUDA_CHECK(cudaGetLastError());
-  if (vec) MK_CUDA_CHECK(launch_k(sampler_collect_kernel<true>, grid, dim3(SAMP_THREADS), 0, st, final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP));
-  else MK_CUDA_CHECK(launch_k(sampler_collect_kernel<false>, grid, dim3(SAMP_THREADS), 0, st, final_scores, cells, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP));
+  if (mode == MODE_FLAT_VEC) MK_CUDA_CHECK(launch_k(sampler_collect_kernel<MODE_FLAT_VEC>, grid, dim3(SAMP_THREADS), 0, st, final_scores, N, pitch, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP));
+  else if (mode == MODE_ROW_VEC) MK_CUDA_CHECK(launch_k(sampler_collect_kernel<MODE_ROW_VEC>, grid, dim3(SAMP_THREADS), 0, st, final_scores, N, pitch, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP));
+  else MK_CUDA_CHECK(launch_k(sampler_collect_kernel<MODE_SCALAR>, grid, dim3(SAMP_THREADS), 0, st, final_scores, N, pitch, IM, seed, thr, inv_tau, cand, cnt, CAND_CAP));
   MK_CUDA_CHECK(cudaGetLastError());
   if (n_sample > 4 * SEL_THREADS) { set_last_error("NUM_SAMPLED_MATCHES %d too large", n_sample); return MK_ERR_UNSUPPORTED; }
   MK_CUDA_CHECK(launch_k(sampler_select_kernel<CAND_CAP>, dim3((unsigned)streams), dim3(SEL_THREADS), 0, st, cand, cnt, n_sample, idx_out, status));
@@ -455,8 +522,8 @@ __device__ __forceinline__ void inv3x3(const float* K, float* Ki) {
 __global__ void ransac_gather_kernel(const int* __restrict__ idx, const float* __restrict__ fs,
                                      const float* __restrict__ kps0, const float* __restrict__ d0,
                                      const float* __restrict__ kps1, const float* __restrict__ d1,
-                                     const float* __restrict__ K0, const float* __restrict__ K1, int N, int IM, int n_s,
-                                     float* __restrict__ xyw) {
+                                     const float* __restrict__ K0, const float* __restrict__ K1, int N, long long pitch, int IM,
+                                     int n_s, float* __restrict__ xyw) {
   pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
   pdl_trigger();
   const int s = blockIdx.x, b = s / IM;
@@ -475,7 +542,7 @@ __global__ void ransac_gather_kernel(const int* __restrict__ idx, const float* _
       o[r * n_s + i] = z0 * (Ki0[r * 3] * u0 + Ki0[r * 3 + 1] * v0 + Ki0[r * 3 + 2]);
       o[(3 + r) * n_s + i] = z1 * (Ki1[r * 3] * u1 + Ki1[r * 3 + 1] * v1 + Ki1[r * 3 + 2]);
     }
-    o[6 * n_s + i] = fs[(long long)b * N * N + cell];
+    o[6 * n_s + i] = fs[(long long)b * N * pitch + (long long)i0 * pitch + i1];
   }
 }
 
@@ -842,14 +909,14 @@ int seed_advance(unsigned long long* s, cudaStream_t st) {
   return MK_OK;
 }
 
-int ransac_solve(const float* final_scores, const float* kps0, const float* d0, const float* kps1, const float* d1,
+int ransac_solve(const float* final_scores, long long pitch, const float* kps0, const float* d0, const float* kps1, const float* d1,
                  const float* K0, const float* K1, int B, int N, const RansacParams& rp, const int* outer_idx,
                  const int* inner_idx, float* xyw, float* hyp_scores, float* hyp_Rt, int* status, float* pose,
                  int* best_set, float* inl_mask, int* best_hyp, cudaStream_t st) {
   const int IM = rp.it_matches, IR = rp.it_ransac, n_s = rp.n_sample;
   if (rp.n_corr != 3) { set_last_error("NUM_CORR_3D_3D must be 3 (got %d)", rp.n_corr); return MK_ERR_UNSUPPORTED; }
   if (n_s % HYP_THREADS) { set_last_error("NUM_SAMPLED_MATCHES must be a multiple of %d", HYP_THREADS); return MK_ERR_UNSUPPORTED; }
-  MK_CUDA_CHECK(launch_k(ransac_gather_kernel, dim3(B * IM, ceil_div(n_s, 256)), dim3(256), 0, st, outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, IM, n_s, xyw));
+  MK_CUDA_CHECK(launch_k(ransac_gather_kernel, dim3(B * IM, ceil_div(n_s, 256)), dim3(256), 0, st, outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, pitch, IM, n_s, xyw));
   MK_CUDA_CHECK(cudaGetLastError());
   const int hyp_per_block = 8;
   const size_t smem_h = (size_t)7 * n_s * 4, smem_f = (size_t)6 * n_s * 4;

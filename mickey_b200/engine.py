@@ -24,6 +24,21 @@ KPAD = 640
 PATCH = 14
 
 
+def nn_pitch(N: int) -> int:
+    """Row pitch (floats) of the N x N outputs the engine allocates: N rounded up to 32, so that every row starts on a
+    128-byte line and the matcher's outputs can leave through TMA tensor stores (N = 1938 rows are only 8-byte aligned).
+    The tensors handed out are the [.., :N] views; MICKEY_NN_CONTIGUOUS=1 keeps the reference's contiguous layout."""
+    import os
+    if os.environ.get("MICKEY_NN_CONTIGUOUS") == "1":
+        return N
+    return (N + 31) // 32 * 32
+
+
+def nn_empty(B: int, N: int, device):
+    """fp32 [B, N, N] view of a [B, N, nn_pitch(N)] buffer."""
+    return torch.empty(B, N, nn_pitch(N), device=device)[:, :, :N]
+
+
 def make_mk_config(cfg) -> _lib.MkConfig:
     variant = backbone_variant(cfg)
     D, depth, heads = VARIANTS[variant]
@@ -355,10 +370,10 @@ class Engine:
     def match(self, B: int, N: int, lean: bool = False):
         """lean: only final_scores (the matrix the solver reads) is materialised; scores / kp_scores come back as None."""
         dev = self.device
-        scores = None if lean else torch.empty(B, N, N, device=dev)
-        kp_scores = None if lean else torch.empty(B, N, N, device=dev)
-        final = torch.empty(B, N, N, device=dev)
-        _lib.check(self.lib.mk_match(self.h, B, _lib.ptr(scores), _lib.ptr(kp_scores), _lib.ptr(final),
+        scores = None if lean else nn_empty(B, N, dev)
+        kp_scores = None if lean else nn_empty(B, N, dev)
+        final = nn_empty(B, N, dev)
+        _lib.check(self.lib.mk_match(self.h, B, _lib.ptr(scores), _lib.ptr(kp_scores), _lib.ptr(final), final.stride(1),
                                      _lib.ptr(self.ws), self.ws.numel(), self._stream()), "mk_match")
         return scores, kp_scores, final
 
@@ -371,8 +386,8 @@ class Engine:
             "images": torch.empty(2 * B, H, W, 3, dtype=torch.uint8, device=dev) if u8 else f(2 * B, 3, H, W),
             "K0": f(B, 3, 3), "K1": f(B, 3, 3),
             "kps": f(2 * B, 2, N), "depth": f(2 * B, 1, N), "scr": f(2 * B, 1, N), "dsc": f(2 * B, c.desc_dim, N),
-            "scores": None if lean else f(B, N, N), "kp_scores": None if lean else f(B, N, N),
-            "final_scores": f(B, N, N), "pose": f(B, 13),
+            "scores": None if lean else nn_empty(B, N, dev), "kp_scores": None if lean else nn_empty(B, N, dev),
+            "final_scores": nn_empty(B, N, dev), "pose": f(B, 13),
             "best_set": torch.empty(B, dtype=torch.int32, device=dev), "inlier_mask": f(B, c.num_sampled),
             "sampled_idx": torch.empty(B * c.it_matches, c.num_sampled, dtype=torch.int32, device=dev),
             "status": torch.zeros(1, dtype=torch.int32, device=dev),
@@ -384,7 +399,7 @@ class Engine:
         _lib.check(fn(
             self.h, _lib.ptr(st["images"]), _lib.ptr(st["K0"]), _lib.ptr(st["K1"]), B, H, W, C.c_ulonglong(seed),
             _lib.ptr(st["kps"]), _lib.ptr(st["depth"]), _lib.ptr(st["scr"]), _lib.ptr(st["dsc"]), _lib.ptr(st["scores"]),
-            _lib.ptr(st["kp_scores"]), _lib.ptr(st["final_scores"]), _lib.ptr(st["pose"]), _lib.ptr(st["best_set"]),
+            _lib.ptr(st["kp_scores"]), _lib.ptr(st["final_scores"]), st["final_scores"].stride(1), _lib.ptr(st["pose"]), _lib.ptr(st["best_set"]),
             _lib.ptr(st["inlier_mask"]), _lib.ptr(st["sampled_idx"]), _lib.ptr(st["status"]), _lib.ptr(ws), ws.numel(),
             self._stream()), "mk_forward")
 
@@ -470,8 +485,11 @@ class Engine:
         ent["done"].record(main)
 
     def solve(self, final_scores, kps, depth, K0, K1, seed: int, outer_idx=None, inner_idx=None, want_extras=False):
-        """kps [2B,2,N], depth [2B,1,N] as produced by extract (image0 rows first)."""
+        """kps [2B,2,N], depth [2B,1,N] as produced by extract (image0 rows first).  final_scores [B,N,N] may be a padded
+        view (last dim contiguous, rows `stride(1)` floats apart) or any tensor (made contiguous)."""
         B, N, _ = final_scores.shape
+        if final_scores.stride(2) != 1 or final_scores.stride(0) != N * final_scores.stride(1):
+            final_scores = final_scores.contiguous()
         dev = self.device
         c = self.mkcfg
         pose = torch.empty(B, 13, device=dev)
@@ -487,7 +505,7 @@ class Engine:
         K0 = K0.to(dev, torch.float32).contiguous()
         K1 = K1.to(dev, torch.float32).contiguous()
         _lib.check(self.lib.mk_solve_pose(
-            self.h, _lib.ptr(final_scores), _lib.ptr(kps), _lib.ptr(depth), _lib.ptr(K0), _lib.ptr(K1), B, N,
+            self.h, _lib.ptr(final_scores), final_scores.stride(1), _lib.ptr(kps), _lib.ptr(depth), _lib.ptr(K0), _lib.ptr(K1), B, N,
             C.c_ulonglong(seed & (2 ** 64 - 1)), _lib.ptr(outer_idx), _lib.ptr(inner_idx), _lib.ptr(pose),
             _lib.ptr(best_set), _lib.ptr(mask), _lib.ptr(sampled), _lib.ptr(hyp), _lib.ptr(status),
             _lib.ptr(self.ws), self.ws.numel(), self._stream()), "mk_solve_pose")

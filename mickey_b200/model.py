@@ -69,7 +69,7 @@ class e2eProbabilisticProcrustesSolver:
 
     def estimate_pose_vectorized(self, batch, return_inliers=False, outer_idx=None, inner_idx=None, seed=None):
         eng = self._owner._engine()
-        final = batch["final_scores"].detach().float().contiguous()
+        final = batch["final_scores"].detach().float()      # a padded-pitch view goes to the kernels as it is
         B, N, _ = final.shape
         kps = torch.cat([batch["kps0"], batch["kps1"]], 0).detach().float().contiguous()
         depth = torch.cat([batch["depth_kp0"], batch["depth_kp1"]], 0).detach().float().contiguous()
@@ -92,7 +92,7 @@ class e2eProbabilisticProcrustesSolver:
         mask = res["inlier_mask"] > 0.5
         i0, i1 = torch.div(cells, N, rounding_mode="trunc"), cells % N
         bidx = torch.arange(B, device=final.device)[:, None].expand(-1, n_s)
-        w = final.reshape(B, N * N)[bidx, cells]
+        w = final[bidx, i0, i1]
         rows = torch.cat([batch["kps0"][bidx, :, i0], batch["kps1"][bidx, :, i1], w[..., None],
                           batch["depth_kp0"][bidx, :, i0], batch["depth_kp1"][bidx, :, i1]], dim=-1)
         zero_pose = bool((res["status"].item() & 5) != 0)
@@ -251,7 +251,7 @@ class MickeyRelativePose(nn.Module):
         mask = st["inlier_mask"] > 0.5
         i0, i1 = torch.div(cells, N, rounding_mode="trunc"), cells % N
         bidx = torch.arange(B, device=cells.device)[:, None].expand(-1, n_s)
-        w = data["final_scores"].reshape(B, N * N)[bidx, cells]
+        w = data["final_scores"][bidx, i0, i1]
         rows = torch.cat([data["kps0"][bidx, :, i0], data["kps1"][bidx, :, i1], w[..., None],
                           data["depth_kp0"][bidx, :, i0], data["depth_kp1"][bidx, :, i1]], dim=-1)
         if int(st["status"].item()) & 5:

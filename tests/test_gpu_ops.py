@@ -262,7 +262,7 @@ def test_linear_attention():
         assert rel_err(got, ref) < 2e-3, g
 
 
-def _matcher(d0, d1, s0, s1, T, dust, lean=False):
+def _matcher(d0, d1, s0, s1, T, dust, lean=False, pitch=None):
     """The three launches of the matcher through the operator-level ABI: EPI_LSE (row + column partials from one pass
     over S), mk_op_matcher_reduce, EPI_DUAL."""
     lib = _lib.load()
@@ -281,12 +281,20 @@ def _matcher(d0, d1, s0, s1, T, dust, lean=False):
     common = dict(groups=B, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=1 / T, part_ld=npad)
     gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
     _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), B, N, npad, _lib.ptr(lr), _lib.ptr(lc), stream()))
-    fin = torch.zeros(B, N, N, device=DEV)
+    # pitch None: the reference's contiguous [B, N, N] (st.global path); otherwise [B, N, pitch][:, :, :N] views: with
+    # pitch % 4 == 0 the outputs leave through TMA tensor stores.  The pad columns must stay untouched (-7).
+    def out():
+        return torch.zeros(B, N, N, device=DEV) if pitch is None else torch.full((B, N, pitch), -7.0, device=DEV)[:, :, :N]
+    fin = out()
+    common["out_pitch"] = fin.stride(1)
     if lean:
         gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, final_scores=fin, **common)
         return None, None, fin, lr, lc
-    sc, kp = torch.zeros(B, N, N, device=DEV), torch.zeros(B, N, N, device=DEV)
+    sc, kp = out(), out()
     gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
+    if pitch is not None:
+        for t in (sc, kp, fin):
+            assert bool((t._base[:, :, N:] == -7.0).all()), "pad columns were written"
     return sc, kp, fin, lr, lc
 
 
@@ -321,6 +329,12 @@ def test_matcher_epilogues_vs_dual_softmax(B, N):
     # lean mode (scores / kp_scores NULL): final_scores is bit-identical
     _, _, fin2, _, _ = _matcher(d0, d1, s0, s1, T, dust, lean=True)
     assert torch.equal(fin, fin2)
+    # padded row pitch (16-byte aligned rows) -> TMA tensor stores: bit-identical to the st.global path, pad untouched
+    pitch = (N + 31) // 32 * 32
+    sc3, kp3, fin3, _, _ = _matcher(d0, d1, s0, s1, T, dust, pitch=pitch)
+    assert torch.equal(sc3, sc) and torch.equal(kp3, kp) and torch.equal(fin3, fin)
+    _, _, fin4, _, _ = _matcher(d0, d1, s0, s1, T, dust, lean=True, pitch=pitch + 4)
+    assert torch.equal(fin4, fin)
 
 
 @pytest.mark.parametrize("scale,T,use_dust", [(6.0, 0.1, True), (6.0, 0.1, False), (1.0, 0.01, False), (40.0, 1.0, True)])
@@ -411,7 +425,7 @@ def test_outer_sampler_is_topk_of_the_race(mode, N):
     ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
     idx = torch.full((B * IM, n_s), -1, dtype=torch.int32, device=DEV)
     status = torch.zeros(1, dtype=torch.int32, device=DEV)
-    _lib.check(lib.mk_op_sample(_lib.ptr(p.to(DEV)), B, N, IM, n_s, seed, _lib.ptr(ws), ws_bytes, _lib.ptr(idx), _lib.ptr(status), stream()))
+    _lib.check(lib.mk_op_sample(_lib.ptr(p.to(DEV)), B, N, 0, IM, n_s, seed, _lib.ptr(ws), ws_bytes, _lib.ptr(idx), _lib.ptr(status), stream()))
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     idx = idx.cpu().numpy().reshape(B, IM, n_s)
@@ -433,6 +447,32 @@ def test_outer_sampler_is_topk_of_the_race(mode, N):
             assert np.all(got[1:] > got[:-1])   # canonical order of a draw: ascending cell index
 
 
+@pytest.mark.parametrize("N,pitch", [(150, 160), (150, 152), (151, 153), (149, 149), (1938, 1952)])
+def test_outer_sampler_does_not_depend_on_the_row_pitch(N, pitch):
+    """final_scores as a padded-pitch view ([N, pitch][:, :N], what the matcher's TMA path writes; 16-byte 4-cell slots
+    per row), as an odd pitch (scalar path) and contiguous (flat 16-byte loads when N*N % 4 == 0): the logical cell index
+    does not depend on the layout, so the same seed gives the identical draw; garbage in the pad columns is never read."""
+    lib = _lib.load()
+    B, IM, n_s = 2, 8, 2048
+    g = torch.Generator().manual_seed(3)
+    p = (torch.rand(B, N, N, generator=g) * 1e-6).to(DEV)
+    p[p < 2e-7] = 0
+    padded = torch.full((B, N, pitch), 1e3, device=DEV)           # a pad that would dominate every draw if it were read
+    padded[:, :, :N] = p
+    ws_bytes = lib.mk_op_sample_workspace_bytes(B, IM)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = []
+    for t, pt in ((p.contiguous(), 0), (padded, pitch)):
+        idx = torch.full((B * IM, n_s), -1, dtype=torch.int32, device=DEV)
+        _lib.check(lib.mk_op_sample(_lib.ptr(t), B, N, pt, IM, n_s, 4321, _lib.ptr(ws), ws_bytes, _lib.ptr(idx), _lib.ptr(status), stream()))
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        out.append(idx.clone())
+    assert torch.equal(out[0], out[1])
+    assert int(out[0].max()) < N * N and float(p.reshape(B, -1)[0][out[0][0].long()].min()) > 0
+
+
 def test_outer_sampler_properties():
     """Exponential-race sampler: distinct cells, never a zero-probability cell, heavy cells (almost) always
     drawn, light cells drawn in proportion to their mass."""
@@ -450,7 +490,7 @@ def test_outer_sampler_properties():
     ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
     idx = torch.full((B * IM, n_s), -1, dtype=torch.int32, device=DEV)
     status = torch.zeros(1, dtype=torch.int32, device=DEV)
-    _lib.check(lib.mk_op_sample(_lib.ptr(p), B, N, IM, n_s, 1234, _lib.ptr(ws), ws_bytes, _lib.ptr(idx), _lib.ptr(status), stream()))
+    _lib.check(lib.mk_op_sample(_lib.ptr(p), B, N, 0, IM, n_s, 1234, _lib.ptr(ws), ws_bytes, _lib.ptr(idx), _lib.ptr(status), stream()))
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     idx = idx.long().cpu()
@@ -468,12 +508,12 @@ def test_outer_sampler_properties():
     p2 = torch.full((1, cells), 1e-6)
     p2[0, : cells // 2] = 2e-6
     p2 = p2.to(DEV)
-    _lib.check(lib.mk_op_sample(_lib.ptr(p2), 1, N, IM, n_s, 99, _lib.ptr(ws), ws_bytes, _lib.ptr(idx := torch.zeros(IM, n_s, dtype=torch.int32, device=DEV)), _lib.ptr(status), stream()))
+    _lib.check(lib.mk_op_sample(_lib.ptr(p2), 1, N, 0, IM, n_s, 99, _lib.ptr(ws), ws_bytes, _lib.ptr(idx := torch.zeros(IM, n_s, dtype=torch.int32, device=DEV)), _lib.ptr(status), stream()))
     torch.cuda.synchronize()
     frac_heavy = float((idx.long() < cells // 2).float().mean())
     assert abs(frac_heavy - 2 / 3) < 0.03, frac_heavy
     # same seed -> same draw (counter-based generator), different seed -> different draw
     idx_b = torch.zeros(IM, n_s, dtype=torch.int32, device=DEV)
-    _lib.check(lib.mk_op_sample(_lib.ptr(p2), 1, N, IM, n_s, 99, _lib.ptr(ws), ws_bytes, _lib.ptr(idx_b), _lib.ptr(status), stream()))
+    _lib.check(lib.mk_op_sample(_lib.ptr(p2), 1, N, 0, IM, n_s, 99, _lib.ptr(ws), ws_bytes, _lib.ptr(idx_b), _lib.ptr(status), stream()))
     torch.cuda.synchronize()
     assert torch.equal(idx, idx_b)

@@ -95,12 +95,16 @@ sc, kp, fin = (torch.empty(1, N, N, device=dev) for _ in range(3))
 common = dict(groups=1, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, part_ld=NP)
 lse = lambda: gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
 red = lambda: _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), 1, N, NP, _lib.ptr(lr), _lib.ptr(lc), stream()))
-dual = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, **common)
-dual_lean = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, final_scores=fin, **common)
+PITCH = (N + 31) // 32 * 32
+scp, kpp, finp = (torch.empty(1, N, PITCH, device=dev)[:, :, :N] for _ in range(3))       # 128-byte aligned rows: TMA tensor stores
+dual_c = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=sc, kp_scores=kp, final_scores=fin, out_pitch=N, **common)
+dual = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=scp, kp_scores=kpp, final_scores=finp, out_pitch=PITCH, **common)
+dual_lean = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, final_scores=finp, out_pitch=PITCH, **common)
 lse(); red()
 report("match.lse (rows + columns)", timeit(lse), 2 * N * N * 384)
 report("match.reduce", timeit(red), nbytes=(NP // 64 + NP // 32) * NP * 8)
-report("match.dual_softmax", timeit(dual), nbytes=3 * N * N * 4 + 2 * N * 384 * 2)
+report("match.dual_softmax (contiguous, st.global)", timeit(dual_c), nbytes=3 * N * N * 4 + 2 * N * 384 * 2)
+report("match.dual_softmax (pitch 1952, TMA stores)", timeit(dual), nbytes=3 * N * N * 4 + 2 * N * 384 * 2)
 report("match.dual_softmax (lean)", timeit(dual_lean), nbytes=N * N * 4 + 2 * N * 384 * 2)
 report("matcher, all three launches", timeit(lambda: (lse(), red(), dual())), nbytes=3 * N * N * 4 + 2 * N * 128 * 4 + 2 * N * 4)
 wr = torch.empty(32 * 3 * N * N, device=dev)
@@ -114,5 +118,5 @@ nb = lib.mk_op_sample_workspace_bytes(1, 8)
 ws = torch.zeros(nb, dtype=torch.uint8, device=dev)
 idx = torch.zeros(8, 2048, dtype=torch.int32, device=dev)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
-report("solve.sample_outer (8 streams)", timeit(lambda: _lib.check(lib.mk_op_sample(_lib.ptr(p), 1, N, 8, 2048, 77, _lib.ptr(ws), nb, _lib.ptr(idx), _lib.ptr(status), stream())), iters=20),
+report("solve.sample_outer (8 streams)", timeit(lambda: _lib.check(lib.mk_op_sample(_lib.ptr(p), 1, N, 0, 8, 2048, 77, _lib.ptr(ws), nb, _lib.ptr(idx), _lib.ptr(status), stream())), iters=20),
        nbytes=N * N * 4)

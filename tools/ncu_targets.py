@@ -82,8 +82,9 @@ if "dual_b" in which:       # the matcher at batch 8 (2048 tiles -> persistent k
     pr, pc = torch.zeros(Bm, NP // 64, NP, 2, device=dev), torch.zeros(Bm, NP // 32, NP, 2, device=dev)
     lr, lc = torch.zeros(Bm, NP, device=dev), torch.zeros(Bm, NP, device=dev)
     s0, s1 = torch.rand(Bm, N, device=dev), torch.rand(Bm, N, device=dev)
-    sc, kp, fin = (torch.empty(Bm, N, N, device=dev) for _ in range(3))
-    common = dict(groups=Bm, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, part_ld=NP)
+    PITCH = N if os.environ.get("NCU_DUAL_CONTIGUOUS") == "1" else (N + 31) // 32 * 32
+    sc, kp, fin = (torch.empty(Bm, N, PITCH, device=dev)[:, :, :N] for _ in range(3))
+    common = dict(groups=Bm, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, part_ld=NP, out_pitch=PITCH)
     for _ in range(reps):
         gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
         _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), Bm, N, NP, _lib.ptr(lr), _lib.ptr(lc), stream()))
@@ -129,7 +130,7 @@ if "sampler" in which:
     idx = torch.zeros(8, 2048, dtype=torch.int32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     for _ in range(reps):
-        _lib.check(lib.mk_op_sample(_lib.ptr(p), 1, N, 8, 2048, 77, _lib.ptr(ws), nb, _lib.ptr(idx), _lib.ptr(status), stream()))
+        _lib.check(lib.mk_op_sample(_lib.ptr(p), 1, N, 0, 8, 2048, 77, _lib.ptr(ws), nb, _lib.ptr(idx), _lib.ptr(status), stream()))
 if "linattn" in which:
     h2, w2, G = 53, 40, 4
     qkv = torch.randn(2 * h2 * w2, G * 384, device=dev)
