@@ -253,24 +253,61 @@ __device__ __forceinline__ void resid_ln_pass3(const GemmParams& p, int row0, in
   }
 }
 
-template <int EPI, int W>
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int row0, int lane, int col_base,
-                                              const float* __restrict__ stage, float mean_l, float rstd_l) {
-  constexpr int CPL = W / 32;
-  constexpr int LDS = W + 4;
-  constexpr int RB = 8;                  // rows per batch: all global loads of a batch are issued before any store
-  const int col = col_base + lane * CPL;
-  float bias[CPL], gam[CPL], bet[CPL];
+// Lane layout of the staged epilogue: a lane owns EIGHT consecutive columns (one 16-byte fp16 store, two 16-byte fp32
+// accesses) of one row per step; W/8 lanes cover a row, so a warp instruction covers 32/(W/8) whole rows.  The first
+// version gave a lane 1-2 columns of every row: 4-byte stores, per-row predicates, 64-bit index math and run-time
+// activation branches made it ~37 SASS instructions per output element, and ncu showed the ViT-B GEMMs epilogue-bound
+// (tensor pipe 33 % active in mlp.fc1, 45 % in attn.qkv, profiles/r02_notes.md); this form is ~3 per element.
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8h(__half* p, const float (&v)[8]) {
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void ld8h(const __half* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) { bias[i] = 0.f; gam[i] = 1.f; bet[i] = 0.f; }
-  if constexpr (EPI == EPI_STORE_H || EPI == EPI_CONV) { if (p.bias) ldg_f<CPL>(p.bias + (size_t)g * p.bias_group_off + col, bias); }
-  if constexpr (EPI == EPI_RESID_F) { ldg_f<CPL>(p.bias + col, bias); ldg_f<CPL>(p.gamma + col, gam); }
-  if constexpr (EPI == EPI_LN) { ldg_f<CPL>(p.gamma + (size_t)g * p.ln_group_off + col, gam); ldg_f<CPL>(p.beta + (size_t)g * p.ln_group_off + col, bet); }
+  for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+
+template <int EPI, int W, int ACT>
+__device__ __forceinline__ void epilogue_rows_impl(const GemmParams& p, int g, int row0, int lane, int col_base,
+                                                   const float* __restrict__ stage, float mean_l, float rstd_l) {
+  constexpr int LDS = W + 4;
+  constexpr int LPR = W / 8;             // lanes per row
+  constexpr int RPS = 32 / LPR;          // rows per step
+  constexpr int STEPS = 32 / RPS;
+  constexpr bool GLOBAL_IN = (EPI == EPI_RESID_F || EPI == EPI_PATCH || EPI == EPI_CONV || EPI == EPI_LN);
+  constexpr int U = GLOBAL_IN ? 2 : 4;   // steps whose loads are all issued before the first store
+  static_assert(W % 8 == 0 && 32 % LPR == 0 && STEPS % U == 0, "staged epilogue: W in {32, 64}");
+  const int seg = lane % LPR, rsub = lane / LPR;
+  const int col = col_base + seg * 8;
+  float bias[8], gam[8], bet[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { bias[i] = 0.f; gam[i] = 1.f; bet[i] = 0.f; }
+  if constexpr (EPI == EPI_STORE_H || EPI == EPI_CONV) { if (p.bias) ldg8(p.bias + (size_t)g * p.bias_group_off + col, bias); }
+  if constexpr (EPI == EPI_RESID_F) { ldg8(p.bias + col, bias); ldg8(p.gamma + col, gam); }
+  if constexpr (EPI == EPI_LN) { ldg8(p.gamma + (size_t)g * p.ln_group_off + col, gam); ldg8(p.beta + (size_t)g * p.ln_group_off + col, bet); }
   const bool use_aux = (EPI == EPI_CONV) && p.aux && ((p.aux_group_mask >> g) & 1);
   const bool use_res = (EPI == EPI_CONV) && p.res_h;
   const bool ln_res = (EPI == EPI_LN) && p.out_f;
   const int rows = min(32, p.M - row0);
-  // per-row index math is done once by lane r (for row r) and broadcast with a shuffle inside the loop
+  // per-row index math is done once by lane r (for row r) and fetched with a shuffle
   int my_pos = 0, my_valid = 1, my_orow = 0;
   {
     const int mr = row0 + lane;
@@ -283,74 +320,93 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int ro
       my_orow = img * (p.tok_per_img + 1) + 1 + my_pos;  // row of the token matrix (cls rows skipped)
     }
   }
-  for (int r0 = 0; r0 < rows; r0 += RB) {
-    float v[RB][CPL], x[RB][CPL], a[RB][CPL];
-    int pos[RB], orow[RB];
-    bool valid[RB];
-    // ---- phase 1: staged accumulators + every global operand of the batch (independent loads in flight)
+  float* out_f = p.out_f ? p.out_f + (size_t)g * p.out_f_group_off + col : nullptr;
+  __half* out_h = p.out_h ? p.out_h + (size_t)g * p.out_h_group_off + col : nullptr;
+#pragma unroll 1
+  for (int s0 = 0; s0 < STEPS; s0 += U) {
+    float v[U][8], x[U][8], a[U][8];
+    int pos[U], orow[U];
+    bool valid[U], live[U];
+    float mean[U], rstd[U];
+    // ---- phase 1: staged accumulators + every global operand of the U steps (independent loads in flight)
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int r = r0 + i;                              // r < 32 always; rows beyond `rows` are loaded from smem only
-      const int m = row0 + r;
-      const bool live = r < rows;
-      ld_f<CPL>(stage + r * LDS + lane * CPL, v[i]);
-      pos[i] = __shfl_sync(0xffffffffu, my_pos, r);
-      orow[i] = __shfl_sync(0xffffffffu, my_orow, r);
-      valid[i] = __shfl_sync(0xffffffffu, my_valid, r) != 0;
+    for (int u = 0; u < U; ++u) {
+      const int r = (s0 + u) * RPS + rsub;
+      const size_t m = (size_t)(row0 + r);
+      live[u] = r < rows;
+      ld8(stage + r * LDS + seg * 8, v[u]);
+      pos[u] = __shfl_sync(0xffffffffu, my_pos, r);
+      orow[u] = __shfl_sync(0xffffffffu, my_orow, r);
+      valid[u] = __shfl_sync(0xffffffffu, my_valid, r) != 0;
+      mean[u] = 0.f; rstd[u] = 0.f;
+      if constexpr (EPI == EPI_LN) { mean[u] = __shfl_sync(0xffffffffu, mean_l, r); rstd[u] = __shfl_sync(0xffffffffu, rstd_l, r); }
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) { x[i][k] = 0.f; a[i][k] = 0.f; }
-      if (live) {
-        if constexpr (EPI == EPI_RESID_F) ld_f<CPL>(p.out_f + (size_t)m * p.out_f_ld + col, x[i]);
-        if constexpr (EPI == EPI_PATCH) ldg_f<CPL>(p.aux + (size_t)pos[i] * p.N + col, a[i]);
+      for (int k = 0; k < 8; ++k) { x[u][k] = 0.f; a[u][k] = 0.f; }
+      if (live[u]) {
+        if constexpr (EPI == EPI_RESID_F) ld8(out_f + m * p.out_f_ld, x[u]);
+        if constexpr (EPI == EPI_PATCH) ldg8(p.aux + (size_t)pos[u] * p.N + col, a[u]);
         if constexpr (EPI == EPI_CONV) {
-          if (use_res) ld_h<CPL>(p.res_h + (size_t)g * p.res_h_group_off + (size_t)m * p.res_h_ld + col, x[i]);
-          if (use_aux) ldg_f<CPL>(p.aux + (size_t)pos[i] * p.N + col, a[i]);
+          if (use_res) ld8h(p.res_h + (size_t)g * p.res_h_group_off + m * p.res_h_ld + col, x[u]);
+          if (use_aux) ldg8(p.aux + (size_t)pos[u] * p.N + col, a[u]);
         }
-        if constexpr (EPI == EPI_LN) { if (ln_res) ld_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, x[i]); }
+        if constexpr (EPI == EPI_LN) { if (ln_res) ld8(out_f + m * p.out_f_ld, x[u]); }
       }
     }
     // ---- phase 2: arithmetic + stores
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int r = r0 + i;
-      const int m = row0 + r;
-      if (r >= rows) continue;
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      const int r = (s0 + u) * RPS + rsub;
+      const size_t m = (size_t)(row0 + r);
       if constexpr (EPI == EPI_STORE_H) {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float t = v[i][k] + bias[k];
-          v[i][k] = (p.act == ACT_GELU) ? gelu_erf(t) : ((p.act == ACT_RELU) ? fmaxf(t, 0.f) : t);
+        for (int k = 0; k < 8; ++k) {
+          const float t = v[u][k] + bias[k];
+          v[u][k] = (ACT == ACT_GELU) ? gelu_erf(t) : ((ACT == ACT_RELU) ? fmaxf(t, 0.f) : t);
         }
-        st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v[i]);
+        st8h(out_h + m * p.out_h_ld, v[u]);
       } else if constexpr (EPI == EPI_RESID_F) {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) x[i][k] = fmaf(gam[k], v[i][k] + bias[k], x[i][k]);
-        st_f<CPL>(p.out_f + (size_t)m * p.out_f_ld + col, x[i]);
+        for (int k = 0; k < 8; ++k) x[u][k] = fmaf(gam[k], v[u][k] + bias[k], x[u][k]);
+        st8(out_f + m * p.out_f_ld, x[u]);
       } else if constexpr (EPI == EPI_PATCH) {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) v[i][k] += a[i][k];
-        st_f<CPL>(p.out_f + (size_t)orow[i] * p.out_f_ld + col, v[i]);
+        for (int k = 0; k < 8; ++k) v[u][k] += a[u][k];
+        st8(out_f + (size_t)orow[u] * p.out_f_ld, v[u]);
       } else if constexpr (EPI == EPI_CONV) {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float t = apply_act(v[i][k] + bias[k] + x[i][k], p.act) + a[i][k];
-          v[i][k] = valid[i] ? t : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          float t = v[u][k] + bias[k] + x[u][k];
+          t = ((ACT == ACT_RELU) ? fmaxf(t, 0.f) : ((ACT == ACT_GELU) ? gelu_erf(t) : t)) + a[u][k];
+          v[u][k] = valid[u] ? t : 0.f;
         }
-        if (p.out_f) st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v[i]);
-        if (p.out_h) st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v[i]);
+        if (out_f) st8(out_f + m * p.out_f_ld, v[u]);
+        if (out_h) st8h(out_h + m * p.out_h_ld, v[u]);
       } else if constexpr (EPI == EPI_STORE_F) {
-        st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v[i]);
+        st8(out_f + m * p.out_f_ld, v[u]);
       } else if constexpr (EPI == EPI_LN) {
-        const float mean = __shfl_sync(0xffffffffu, mean_l, r), rstd = __shfl_sync(0xffffffffu, rstd_l, r);
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float t = (v[i][k] - mean) * rstd * gam[k] + bet[k] + x[i][k];
-          v[i][k] = valid[i] ? t : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          const float t = (v[u][k] - mean[u]) * rstd[u] * gam[k] + bet[k] + x[u][k];
+          v[u][k] = valid[u] ? t : 0.f;
         }
-        if (ln_res) st_f<CPL>(p.out_f + (size_t)g * p.out_f_group_off + (size_t)m * p.out_f_ld + col, v[i]);
-        st_h<CPL>(p.out_h + (size_t)g * p.out_h_group_off + (size_t)m * p.out_h_ld + col, v[i]);
+        if (ln_res) st8(out_f + m * p.out_f_ld, v[u]);
+        st8h(out_h + m * p.out_h_ld, v[u]);
       }
     }
+  }
+}
+
+template <int EPI, int W>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, int g, int row0, int lane, int col_base,
+                                              const float* __restrict__ stage, float mean_l, float rstd_l) {
+  // the activation is a compile-time parameter of the body (one uniform branch per call instead of one per element)
+  if constexpr (EPI == EPI_STORE_H || EPI == EPI_CONV) {
+    if (p.act == ACT_GELU) epilogue_rows_impl<EPI, W, ACT_GELU>(p, g, row0, lane, col_base, stage, mean_l, rstd_l);
+    else if (p.act == ACT_RELU) epilogue_rows_impl<EPI, W, ACT_RELU>(p, g, row0, lane, col_base, stage, mean_l, rstd_l);
+    else epilogue_rows_impl<EPI, W, ACT_NONE>(p, g, row0, lane, col_base, stage, mean_l, rstd_l);
+  } else {
+    epilogue_rows_impl<EPI, W, ACT_NONE>(p, g, row0, lane, col_base, stage, mean_l, rstd_l);
   }
 }
 
@@ -465,17 +521,17 @@ __device__ __forceinline__ void dual_store_chunk(const GemmParams& p, int g, int
 // n_valid).  No transposition pass, full 128-byte lines on the way to L2.
 // `stage`: 3 x 4 KB, 1024-byte aligned, warp-private; `aux`: 64 floats (column operands), warp-private.
 __device__ __forceinline__ void dual_store_chunk_tma(const GemmParams& p, const OutMaps& om, int g, int row0, int lane, int n0,
-                                                     const float (&v)[32], float* stage, float* aux, float lr, float s0) {
+                                                     const float (&v)[32], float* stage, float* aux, float lr, float s0,
+                                                     float lc_l, float s1_l) {
+  // lc_l / s1_l: column operands of column n0 + lane (lse of the column, +inf beyond n_valid; keypoint score), loaded by
+  // the caller for all of the warp's chunks at once so that their latency is paid once per tile
   const float k2x2 = 2.0f * p.inv_temp * 1.4426950408889634f;
-  const size_t gv = (size_t)g * p.n_valid;
-  const int col = n0 + lane;
-  const bool col_ok = col < p.n_valid;
   const bool full = p.scores != nullptr;
   // the previous chunk's stores must have finished READING the staging boxes
   if (lane == 0) tma_store_wait_read();
   __syncwarp();
-  aux[lane] = col_ok ? __ldg(p.lse_c + (size_t)g * p.part_ld + col) : -MK_NEG_INF;
-  aux[32 + lane] = col_ok ? __ldg(p.scr1 + gv + col) : 0.0f;
+  aux[lane] = lc_l;
+  aux[32 + lane] = s1_l;
   __syncwarp();
   float4* b_sc = reinterpret_cast<float4*>(stage) + lane * 8;
   float4* b_kp = b_sc + 256;

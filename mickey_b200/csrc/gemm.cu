@@ -188,8 +188,9 @@ static bool use_simt() {
 }
 
 template <int BN, int EPI, int STAGES>
-static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  const OutMaps& om = no_out_maps();
+static int launch_tc(dim3 grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream,
+                     const OutMaps& om = no_out_maps()) {
+  static_assert(EPI != EPI_DUAL || (BN == 128 && STAGES >= 3), "EPI_DUAL / TMA stages its output boxes in a >= 96 KB ring");
   static unsigned long long attr_mask = 0;
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   if (first_use_on_device(attr_mask)) {
@@ -320,12 +321,15 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
     if (rc) return rc;
     if constexpr (EPI == EPI_DUAL) {
       if (p.out_tma) {
-        // the three N x N outputs leave through TMA tensor stores: always the persistent kernel (its staging area holds
-        // the eight warps' 32 x 32 output boxes; one CTA per SM walks the tile list)
+        // the three N x N outputs leave through TMA tensor stores.  One pair (256 tiles): one-tile CTAs, two per SM, all
+        // resident at once (the kernel is latency-bound there); batches: the persistent kernel, one CTA per SM.
         OutMaps om = {};
         float* outs[3] = {p.scores, p.kp_scores, p.final_scores};
         for (int i = 0; i < 3; ++i)
           if (outs[i]) { rc = encode_tensor_map_out_f32(&om.m[i], outs[i], p.n_valid, p.out_pitch, p.groups); if (rc) return rc; }
+        if constexpr (BN == 128) {
+          if ((long long)grid.x * grid.y * grid.z <= 2LL * sm_count()) return launch_tc<BN, EPI, 3>(grid, tmA, tmB, p, stream, om);
+        }
         return launch_persistent<BN, EPI>(grid, tmA, tmB, p, stream, om);
       }
     }

@@ -33,8 +33,8 @@ template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
   // the ring is reused as the epilogue's staging area (8 warps x 32 rows x (BN/2 + 4) floats), which a 2-stage ring
   // does not cover
-  // (EPI_DUAL's TMA path stages 8 x 12 KB of output boxes + 2 KB of column operands there: 98 KB <= the 3-stage ring of 96 KB + slack is
-  // NOT enough, so the matcher runs on the >= 4-stage instantiations or the persistent kernel: see launch_one)
+  // (EPI_DUAL's TMA path: the eight warps' 3 x 4 KB output boxes are exactly the 96 KB of a 3-stage 128 x 128 ring; their column
+  // operands (8 x 64 floats) use the 2 KB statistics block behind the barriers)
   constexpr int ring = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2), staging = 8 * 32 * (BN / 2 + 4) * 4;
   // + row statistics of EPI_RESID_LN (never run on the 2-stage ring, whose three CTAs per SM have no room to spare)
   return (ring > staging ? ring : staging) + 1024 /*align slack*/ + 256 /*barriers*/ + (STAGES == 2 ? 0 : 2048);
@@ -239,10 +239,20 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, const OutMaps
     const float lr = row_ok ? __ldg(p.lse_r + (size_t)g * p.part_ld + m) : -MK_NEG_INF;
     const float s0 = row_ok ? __ldg(p.scr0 + (size_t)g * p.n_valid + m) : 0.0f;
     if (p.out_tma) {
-      for (int c = c_begin; c < c_end; ++c) {
-        if (n0 + c * 32 < p.n_valid && m0 + q * 32 < p.n_valid) {
+      float lc_pre[CPH], s1_pre[CPH];
+#pragma unroll
+      for (int ci = 0; ci < CPH; ++ci) {
+        const int col = n0 + (c_begin + ci) * 32 + lane;
+        const bool ok = col < p.n_valid;
+        lc_pre[ci] = ok ? __ldg(p.lse_c + (size_t)g * p.part_ld + col) : -MK_NEG_INF;
+        s1_pre[ci] = ok ? __ldg(p.scr1 + (size_t)g * p.n_valid + col) : 0.0f;
+      }
+#pragma unroll
+      for (int ci = 0; ci < CPH; ++ci) {
+        const int c = c_begin + ci;
+        if (c < c_end && n0 + c * 32 < p.n_valid && m0 + q * 32 < p.n_valid) {
           tmem_ld32(taddr + c * 32, v);
-          dual_store_chunk_tma(p, om, g, m0 + q * 32, lane, n0 + c * 32, v, dual_stage, dual_aux, lr, s0);
+          dual_store_chunk_tma(p, om, g, m0 + q * 32, lane, n0 + c * 32, v, dual_stage, dual_aux, lr, s0, lc_pre[ci], s1_pre[ci]);
         }
       }
     } else {
@@ -379,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                          reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * (BN / 2 + 4)), [] {},
                          reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)), bar_base + 256,
                          reinterpret_cast<float*>(smem_raw + (base - raw) + warp * DUAL_STAGE_BYTES),
-                         reinterpret_cast<float*>(smem_raw + (base - raw) + 8 * DUAL_STAGE_BYTES) + warp * 64);
+                         reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)) + warp * 64);
   if constexpr (EPI == EPI_DUAL) { if (p.out_tma && lane == 0) tma_store_wait_all(); }   // smem must outlive the bulk reads
 
   tc_fence_before();

@@ -313,7 +313,7 @@ sampler_collect_kernel(const float* __restrict__ fs, int N, long long pitch, int
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float pv = (c == 0) ? v[i].x : (c == 1) ? v[i].y : (c == 2) ? v[i].z : v[i].w;
-          if (rem[i] > c) cell(eb[i] + c, pv);
+          if (MODE == MODE_FLAT_VEC || rem[i] > c) cell(eb[i] + c, pv);      // flat mode: out-of-range slots hold zeros
         }
       }
     } else {
