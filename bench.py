@@ -451,7 +451,7 @@ def main():
     m = measure(wl, depth, n_blocks)
     c2 = None
     if args.workload == "c3" and world == 1 and not args.no_c2:
-        c2 = measure(WORKLOADS["c2"], 3, 9, with_profile=False)
+        c2 = measure(WORKLOADS["c2"], 3, 9, with_profile=True)
 
     if rank != 0:
         if world > 1:
@@ -571,7 +571,8 @@ def main():
                               "ms_per_step_min": d2["ms_per_step_min"], "ms_per_step_max": d2["ms_per_step_max"], "blocks": d2["blocks"],
                               "latency_ms_single_step": c2["lat"]["median_ms"] / lat_steps, "steps_in_flight": c2["depth"],
                               "e2e": {"value": e2["value"], "ms_per_step": e2["ms_per_step"], "h2d_bytes_per_step": int(2 * 3 * H_IMG * W_IMG * 4),
-                                      "d2h_bytes_per_step": 52}, "gpu_launches": c2["launches"]}
+                                      "d2h_bytes_per_step": 52}, "gpu_launches": c2["launches"],
+                              "stage_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(c2["prof"].items(), key=lambda kv: -kv[1]["ms_per_step"])}}
     if world == 1 and not args.no_eager_baseline:
         line["gpu_eager_baseline"] = gpu_eager_run(wl, dev)
     if world == 1 and not args.no_cpu_baseline:

@@ -68,6 +68,17 @@ __device__ __forceinline__ float exp2_fma(float x) {
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2): one issue slot for two logits.  The softmax loop is bound by
+// instruction issue (ncu: 71 % issue-active, MUFU 52 %, FMA 39 %), not by any single pipe.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
+  asm("{\n\t.reg .b64 ra, rd;\n\tmov.b64 rd, {%0, %1};\n\tmov.b64 ra, {%2, %3};\n\tadd.rn.f32x2 rd, rd, ra;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -92,7 +103,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <int POLY>     // every POLY-th pair of logits takes the FMA-pipe exp2 (0: none)
+template <int POLY, int PK>     // every POLY-th pair of logits takes the FMA-pipe exp2 (0: none); PK: packed fp32x2 scale / row sum
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int D, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -243,10 +254,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float x0 = fmaf(s[2 * i], scale_log2, neg_m), x1 = fmaf(s[2 * i + 1], scale_log2, neg_m);
+        float x0, x1;
+        if (PK) fma2(x0, x1, s[2 * i], s[2 * i + 1], scale_log2, neg_m);
+        else { x0 = fmaf(s[2 * i], scale_log2, neg_m); x1 = fmaf(s[2 * i + 1], scale_log2, neg_m); }
         const bool poly = (POLY > 0) && (i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1);   // compile-time after unrolling
         const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
-        sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1;
+        if (PK) { if (i & 1) add2(sa[2], sa[3], p0, p1); else add2(sa[0], sa[1], p0, p1); }
+        else { sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1; }
         __half2 h = __floats2half2_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&h);
       }
@@ -301,21 +315,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
 int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads, cudaStream_t s) {
   if (D != heads * FA_D) { set_last_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads); return MK_ERR_UNSUPPORTED; }
   static unsigned long long attr_mask = 0;
-  static int poly = 0;
+  static int poly = 0, pack = 0;
   if (first_use_on_device(attr_mask)) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    // packed fp32x2 scale / row sum (FFMA2 / FADD2): on by default; with it the best FMA-pipe exp2 share is every 8th pair
+    // (64 images, ViT-B: 1113 us [unpacked, every 4th] -> 1058 us; MICKEY_ATTN_PACK2=0 / MICKEY_ATTN_POLY=0|8|4 override)
+    { const char* e = getenv("MICKEY_ATTN_PACK2"); pack = (e && e[0] == '0') ? 0 : 1; }
     // default: every 4th pair (25 %) on the FMA pipe -- measured 32.0 -> 29.9 us (one 720x540 pair) and 1156 -> 1100 us
     // (64 images, ViT-B); 12.5 % gives half of that, 50 % is slower than none (issue-bound).  MICKEY_ATTN_POLY=0 disables.
-    const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : 4;
+    const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : (pack ? 8 : 4);
   }
   CUtensorMap tm;
   int rc = make_tensor_map_f16(&tm, qkv, (long long)n_img * T, 3LL * D, 3LL * D, FA_BQ);
   if (rc) return rc;
   dim3 grid(ceil_div(T, FA_BQ), heads, n_img);
   const float scale_log2 = 0.125f * 1.4426950408889634f;
-  auto kern = poly == 8 ? attention_tc_kernel<8> : poly == 4 ? attention_tc_kernel<4> : attention_tc_kernel<0>;
+  auto kern = pack ? (poly == 8 ? attention_tc_kernel<8, 1> : poly == 4 ? attention_tc_kernel<4, 1> : attention_tc_kernel<0, 1>)
+                   : (poly == 8 ? attention_tc_kernel<8, 0> : poly == 4 ? attention_tc_kernel<4, 0> : attention_tc_kernel<0, 0>);
   MK_CUDA_CHECK(launch_k(kern, grid, dim3(FA_THREADS), (size_t)FA_SMEM, s, tm, (__half*)out, T, D, scale_log2));
   return MK_OK;
 }
