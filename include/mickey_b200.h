@@ -165,6 +165,7 @@ typedef struct mk_gemm_args {
   const float* lse_r; const float* lse_c;          /* DUAL in: log2-domain log-sum-exp per row / column, [groups, part_ld] (mk_op_matcher_reduce) */
   const float* scr0; const float* scr1;
   float* scores; float* kp_scores; float* final_scores;
+  float lse_bound;         /* LSE: > 0 = every |A.B| <= lse_bound (normalised descriptors): fixed-shift partials; 0 = true maxima */
   long long out_pitch;     /* DUAL: row pitch of the outputs in floats (0 = n_valid); % 4 == 0 selects the TMA-store path */
 } mk_gemm_args;
 

@@ -50,6 +50,7 @@ class MkGemmArgs(C.Structure):
         ("part_row", C.c_void_p), ("part_col", C.c_void_p), ("part_ld", C.c_int),
         ("lse_r", C.c_void_p), ("lse_c", C.c_void_p), ("scr0", C.c_void_p), ("scr1", C.c_void_p),
         ("scores", C.c_void_p), ("kp_scores", C.c_void_p), ("final_scores", C.c_void_p),
+        ("lse_bound", C.c_float),
         ("out_pitch", C.c_longlong),
     ]
 

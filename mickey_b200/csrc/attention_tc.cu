@@ -50,6 +50,19 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// Two 32-column TMEM loads issued back to back with ONE wait (the single-load helper waits after each: ~250 clocks of
+// exposed latency per tile and softmax warp).
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr), "r"(taddr + 32) : "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -211,19 +224,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
     const uint32_t tO = tmem_base + lane_off + FA_COL_O + 32 * half;
     const uint32_t pair_bar = 1 + quad;                     // named barrier of the two warps that share these rows
     float m_ref = -INFINITY, l_run = 0.f;
+    const bool rows_dead = (q0 + quad * 32 >= T);           // every row of this warp lies beyond the sequence (last query tile)
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       float s[64];
-      {
-        float v[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(tS + c * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = v[i];
-        }
-      }
+      tmem_ld64(tS, s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);         // S buffer may be overwritten by QK^T of the next tile
@@ -248,21 +254,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
       float alpha = 1.0f;
       const bool move = (mx > m_ref + 8.0f);       // always true for j == 0 (m_ref = -inf); identical in both halves
       if (move) { alpha = ex2_approx(m_ref - mx); m_ref = mx; }
-      // p = 2^(s*scale - m_ref): one FFMA + one MUFU.EX2 per element, 4 partial sums for ILP
+      // p = 2^(s*scale - m_ref): one FFMA + one MUFU.EX2 per element, 4 partial sums for ILP.
+      // T = 1939 = 15 * 128 + 19: the last key tile holds 19 keys and the last query tile 19 rows.  Groups of 16 logits
+      // that are entirely masked (or whose rows are all beyond T) skip the exponentials: their P is exactly 0 either way
+      // (warp-uniform branches; static register indexing is kept).
+      const int live_groups = rows_dead ? 0 : (valid >= 64 ? 4 : (valid <= 0 ? 0 : (valid + 15) >> 4));
       float sa[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_ref;
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x0, x1;
-        if (PK) fma2(x0, x1, s[2 * i], s[2 * i + 1], scale_log2, neg_m);
-        else { x0 = fmaf(s[2 * i], scale_log2, neg_m); x1 = fmaf(s[2 * i + 1], scale_log2, neg_m); }
-        const bool poly = (POLY > 0) && (i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1);   // compile-time after unrolling
-        const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
-        if (PK) { if (i & 1) add2(sa[2], sa[3], p0, p1); else add2(sa[0], sa[1], p0, p1); }
-        else { sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1; }
-        __half2 h = __floats2half2_rn(p0, p1);
-        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      for (int g8 = 0; g8 < 4; ++g8) {
+        if (g8 < live_groups) {
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const int i = g8 * 8 + ii;
+            float x0, x1;
+            if (PK) fma2(x0, x1, s[2 * i], s[2 * i + 1], scale_log2, neg_m);
+            else { x0 = fmaf(s[2 * i], scale_log2, neg_m); x1 = fmaf(s[2 * i + 1], scale_log2, neg_m); }
+            const bool poly = (POLY > 0) && (i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1);   // compile-time after unrolling
+            const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
+            if (PK) { if (i & 1) add2(sa[2], sa[3], p0, p1); else add2(sa[0], sa[1], p0, p1); }
+            else { sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1; }
+            __half2 h = __floats2half2_rn(p0, p1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        } else {
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) pk[g8 * 8 + ii] = 0u;
+        }
       }
       l_run = l_run * alpha + ((sa[0] + sa[1]) + (sa[2] + sa[3]));     // this thread's key half only
       if (j > 0) {

@@ -64,6 +64,8 @@ struct GemmParams {
   // with tiles = part_ld / 128.  Slot-major, so that both the warps' stores and the reduce kernel's loads coalesce.
   float2* part_row; float2* part_col;
   int part_ld;              // n_valid rounded up to a multiple of 128
+  float lse_bound;          // > 0: every |S| <= lse_bound (L2-normalised descriptors: 1): the partials use the fixed shift
+                            // lse_bound / T instead of true maxima (one exponential per cell, no max reductions)
   // EPI_DUAL in: log2-domain log-sum-exp of every row / column of the dustbin-augmented S/T, [groups, part_ld]
   const float* lse_r; const float* lse_c;
   const float* scr0; const float* scr1; // [groups, n_valid]

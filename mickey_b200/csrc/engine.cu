@@ -373,6 +373,9 @@ int run_match(mk_handle* h, int n_pairs, int N, float* scores, float* kp_scores,
   };
   // pass 1: S once, row and column partials from the same tile; then the tiny fold (+ dustbin); pass 2: outputs
   { GemmParams p = mp(); p.part_row = reinterpret_cast<float2*>(w.part_row); p.part_col = reinterpret_cast<float2*>(w.part_col);
+    // L2-normalised descriptors: |S| <= 1 (+ rounding), so 1.001 / T bounds every logit; used while 2 * 1.001 / T * log2(e)
+    // stays far inside the fp32 exponent range (T >= 0.04); otherwise, and for un-normalised descriptors, true maxima
+    p.lse_bound = (c.norm_dsc && inv_t <= 25.0f) ? 1.001f : 0.0f;
     MK_TRY(gemm(h, "match.lse", EPI_LSE, A0, rows, 384, A1, rows, 384, p, st)); }
   MK_KERNEL("match.reduce", matcher_lse_reduce(w.part_row, w.part_col, dust, n_pairs, N, npad, w.lse_r, w.lse_c, st));
   { GemmParams p = mp(); p.lse_r = w.lse_r; p.lse_c = w.lse_c; p.scr0 = w.scr_copy; p.scr1 = w.scr_copy + (size_t)n_pairs * N;
@@ -638,7 +641,7 @@ int mk_op_gemm(const mk_gemm_args* a, void* stream) {
   p.aux = a->aux; p.aux_group_mask = a->aux_group_mask; p.pad_h2 = a->pad_h2; p.pad_w2 = a->pad_w2; p.tok_per_img = a->tok_per_img;
   p.eps = a->eps; p.n_valid = a->n_valid; p.inv_temp = a->inv_temp; p.dustbin = a->dustbin;
   p.part_row = reinterpret_cast<float2*>(a->part_row); p.part_col = reinterpret_cast<float2*>(a->part_col); p.part_ld = a->part_ld;
-  p.lse_r = a->lse_r; p.lse_c = a->lse_c; p.scr0 = a->scr0; p.scr1 = a->scr1;
+  p.lse_r = a->lse_r; p.lse_c = a->lse_c; p.scr0 = a->scr0; p.scr1 = a->scr1; p.lse_bound = a->lse_bound;
   p.out_pitch = a->out_pitch > 0 ? a->out_pitch : a->n_valid;
   p.out_tma = (a->final_scores && p.out_pitch % 4 == 0 && reinterpret_cast<uintptr_t>(a->final_scores) % 16 == 0 &&
                (!a->scores || (reinterpret_cast<uintptr_t>(a->scores) % 16 == 0 && reinterpret_cast<uintptr_t>(a->kp_scores) % 16 == 0))) ? 1 : 0;

@@ -479,6 +479,27 @@ __device__ __forceinline__ void lse_chunk(const GemmParams& p, int g, int col0, 
   if (col < p.n_valid) p.part_col[((size_t)g * (p.part_ld / 32) + col_slot) * p.part_ld + col] = make_float2(cmax_l, csum_l);
 }
 
+// The same chunk when every |S| is known to be <= p.lse_bound (L2-normalised descriptors, DSC_HEAD.NORM_DSC: True, and a
+// temperature for which 2 * bound / T stays inside the fp32 exponent range): one fixed shift serves rows and columns,
+// so a cell costs ONE exponential and the column partial one transposing sum (no max passes).  Slots hold (shift, sum).
+__device__ __forceinline__ void lse_chunk_bounded(const GemmParams& p, int g, int col0, int lane, int col_slot, bool row_ok,
+                                                  const float (&v)[32], float& rsum) {
+  const float k2 = p.inv_temp * 1.4426950408889634f, sh = p.lse_bound * k2;
+  float t[32];
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float e0 = (row_ok && col0 + j < p.n_valid) ? ex2_approx_f(fmaf(v[j], k2, -sh)) : 0.f;
+    const float e1 = (row_ok && col0 + j + 1 < p.n_valid) ? ex2_approx_f(fmaf(v[j + 1], k2, -sh)) : 0.f;
+    t[j] = e0; t[j + 1] = e1;
+    acc0 += e0; acc1 += e1;
+  }
+  rsum += acc0 + acc1;
+  const float csum_l = warp_rowsum32(t, lane);
+  const int col = col0 + lane;
+  if (col < p.n_valid) p.part_col[((size_t)g * (p.part_ld / 32) + col_slot) * p.part_ld + col] = make_float2(sh, csum_l);
+}
+
 // Pass 2, one 32 x 32 chunk, coalesced: the warp owns rows row0..row0+31 (lane == row on entry).  Each lane evaluates
 // its row's scores with the column terms read from the warp's staging block (broadcast loads), the block is transposed
 // through `stage` ([32][33] floats + 64 floats of column operands, warp-private), then lane == column writes one

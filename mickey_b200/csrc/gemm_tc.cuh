@@ -224,10 +224,20 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, const OutMaps
     static_assert(BN == 128, "matcher epilogues: 128-wide tiles");
     const bool row_ok = m < p.n_valid;
     float rmax = MK_NEG_INF, rsum = 0.f;
-    for (int c = c_begin; c < c_end; ++c) {
-      if (n0 + c * 32 < p.n_valid) {
-        tmem_ld32(taddr + c * 32, v);
-        lse_chunk(p, g, n0 + c * 32, lane, (m0 / BLOCK_M) * 4 + q, row_ok, v, rmax, rsum);
+    if (p.lse_bound > 0.f) {
+      rmax = p.lse_bound * p.inv_temp * 1.4426950408889634f;
+      for (int c = c_begin; c < c_end; ++c) {
+        if (n0 + c * 32 < p.n_valid) {
+          tmem_ld32(taddr + c * 32, v);
+          lse_chunk_bounded(p, g, n0 + c * 32, lane, (m0 / BLOCK_M) * 4 + q, row_ok, v, rsum);
+        }
+      }
+    } else {
+      for (int c = c_begin; c < c_end; ++c) {
+        if (n0 + c * 32 < p.n_valid) {
+          tmem_ld32(taddr + c * 32, v);
+          lse_chunk(p, g, n0 + c * 32, lane, (m0 / BLOCK_M) * 4 + q, row_ok, v, rmax, rsum);
+        }
       }
     }
     release();

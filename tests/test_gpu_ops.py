@@ -262,7 +262,7 @@ def test_linear_attention():
         assert rel_err(got, ref) < 2e-3, g
 
 
-def _matcher(d0, d1, s0, s1, T, dust, lean=False, pitch=None):
+def _matcher(d0, d1, s0, s1, T, dust, lean=False, pitch=None, bound=0.0):
     """The three launches of the matcher through the operator-level ABI: EPI_LSE (row + column partials from one pass
     over S), mk_op_matcher_reduce, EPI_DUAL."""
     lib = _lib.load()
@@ -279,7 +279,7 @@ def _matcher(d0, d1, s0, s1, T, dust, lean=False, pitch=None):
     pc = torch.full((B, npad // 32, npad, 2), float("nan"), device=DEV)
     lr, lc = torch.full((B, npad), float("nan"), device=DEV), torch.full((B, npad), float("nan"), device=DEV)
     common = dict(groups=B, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=1 / T, part_ld=npad)
-    gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
+    gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, lse_bound=bound, **common)
     _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), B, N, npad, _lib.ptr(lr), _lib.ptr(lc), stream()))
     # pitch None: the reference's contiguous [B, N, N] (st.global path); otherwise [B, N, pitch][:, :, :N] views: with
     # pitch % 4 == 0 the outputs leave through TMA tensor stores.  The pad columns must stay untouched (-7).
@@ -333,6 +333,10 @@ def test_matcher_epilogues_vs_dual_softmax(B, N):
     # lean mode (scores / kp_scores NULL): final_scores is bit-identical
     _, _, fin2, _, _ = _matcher(d0, d1, s0, s1, T, dust, lean=True)
     assert torch.equal(fin, fin2)
+    # normalised descriptors: the fixed-shift partials (one exponential per cell) give the same vectors
+    sc5, _, fin5, lr5, lc5 = _matcher(d0, d1, s0, s1, T, dust, bound=1.001)
+    assert float((lr5[:, :N] - lr[:, :N]).abs().max()) < 1e-5 and float((lc5[:, :N] - lc[:, :N]).abs().max()) < 1e-5
+    assert rel_err(sc5, ref) < 1e-4 and rel_err(fin5, fin) < 1e-5
     # padded row pitch (16-byte aligned rows) -> TMA tensor stores: bit-identical to the st.global path, pad untouched
     pitch = (N + 31) // 32 * 32
     sc3, kp3, fin3, _, _ = _matcher(d0, d1, s0, s1, T, dust, pitch=pitch)

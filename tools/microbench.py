@@ -93,7 +93,8 @@ lr, lc = torch.zeros(1, NP, device=dev), torch.zeros(1, NP, device=dev)
 s0, s1 = torch.rand(1, N, device=dev), torch.rand(1, N, device=dev)
 sc, kp, fin = (torch.empty(1, N, N, device=dev) for _ in range(3))
 common = dict(groups=1, a_row_group_off=N, b_row_group_off=N, n_valid=N, inv_temp=10.0, part_ld=NP)
-lse = lambda: gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)
+lse = lambda: gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, lse_bound=1.001, **common)      # normalised descriptors
+lse_max = lambda: gemm("LSE", a0, a1, N, N, 384, part_row=pr, part_col=pc, **common)                   # true row / column maxima
 red = lambda: _lib.check(lib.mk_op_matcher_reduce(_lib.ptr(pr), _lib.ptr(pc), _lib.ptr(dust), 1, N, NP, _lib.ptr(lr), _lib.ptr(lc), stream()))
 PITCH = (N + 31) // 32 * 32
 scp, kpp, finp = (torch.empty(1, N, PITCH, device=dev)[:, :, :N] for _ in range(3))       # 128-byte aligned rows: TMA tensor stores
@@ -101,7 +102,8 @@ dual_c = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, sc
 dual = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, scores=scp, kp_scores=kpp, final_scores=finp, out_pitch=PITCH, **common)
 dual_lean = lambda: gemm("DUAL", a0, a1, N, N, 384, lse_r=lr, lse_c=lc, scr0=s0, scr1=s1, final_scores=finp, out_pitch=PITCH, **common)
 lse(); red()
-report("match.lse (rows + columns)", timeit(lse), 2 * N * N * 384)
+report("match.lse (rows + columns, fixed shift)", timeit(lse), 2 * N * N * 384)
+report("match.lse (rows + columns, true maxima)", timeit(lse_max), 2 * N * N * 384)
 report("match.reduce", timeit(red), nbytes=(NP // 64 + NP // 32) * NP * 8)
 report("match.dual_softmax (contiguous, st.global)", timeit(dual_c), nbytes=3 * N * N * 4 + 2 * N * 384 * 2)
 report("match.dual_softmax (pitch 1952, TMA stores)", timeit(dual), nbytes=3 * N * N * 4 + 2 * N * 384 * 2)
