@@ -262,25 +262,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
       float sa[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_ref;
       uint32_t pk[32];
+      auto exp_pair = [&](int i) {                 // i is a compile-time constant after unrolling
+        float x0, x1;
+        if (PK) fma2(x0, x1, s[2 * i], s[2 * i + 1], scale_log2, neg_m);
+        else { x0 = fmaf(s[2 * i], scale_log2, neg_m); x1 = fmaf(s[2 * i + 1], scale_log2, neg_m); }
+        const bool poly = (POLY > 0) && (i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1);
+        const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
+        if (PK) { if (i & 1) add2(sa[2], sa[3], p0, p1); else add2(sa[0], sa[1], p0, p1); }
+        else { sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1; }
+        __half2 h = __floats2half2_rn(p0, p1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      };
+      if (live_groups == 4) {                      // every tile but the last one: one straight-line block of 32 pairs
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
-        if (g8 < live_groups) {
+        for (int i = 0; i < 32; ++i) exp_pair(i);
+      } else {
 #pragma unroll
-          for (int ii = 0; ii < 8; ++ii) {
-            const int i = g8 * 8 + ii;
-            float x0, x1;
-            if (PK) fma2(x0, x1, s[2 * i], s[2 * i + 1], scale_log2, neg_m);
-            else { x0 = fmaf(s[2 * i], scale_log2, neg_m); x1 = fmaf(s[2 * i + 1], scale_log2, neg_m); }
-            const bool poly = (POLY > 0) && (i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1);   // compile-time after unrolling
-            const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
-            if (PK) { if (i & 1) add2(sa[2], sa[3], p0, p1); else add2(sa[0], sa[1], p0, p1); }
-            else { sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1; }
-            __half2 h = __floats2half2_rn(p0, p1);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (g8 < live_groups) {
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) exp_pair(g8 * 8 + ii);
+          } else {
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) pk[g8 * 8 + ii] = 0u;
           }
-        } else {
-#pragma unroll
-          for (int ii = 0; ii < 8; ++ii) pk[g8 * 8 + ii] = 0u;
         }
       }
       l_run = l_run * alpha + ((sa[0] + sa[1]) + (sa[2] + sa[3]));     // this thread's key half only
@@ -342,12 +347,14 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    // packed fp32x2 scale / row sum (FFMA2 / FADD2): on by default; with it the best FMA-pipe exp2 share is every 8th pair
-    // (64 images, ViT-B: 1113 us [unpacked, every 4th] -> 1058 us; MICKEY_ATTN_PACK2=0 / MICKEY_ATTN_POLY=0|8|4 override)
+    // packed fp32x2 scale / row sum (FFMA2 / FADD2): on by default (64 images, ViT-B: 1113 -> 1081 us with every 4th pair on
+    // the FMA-pipe exp2, 1058 us with every 8th).  Every 4th stays the default: the `scores` parity metric, which amplifies
+    // the features' error through logits of +-10, was consistently better with it (ViT-L 720x540: 7.9e-4 vs 1.03e-3 for
+    // every 8th and 8.6e-4 for none; profiles/r02_notes.md).  MICKEY_ATTN_PACK2=0 / MICKEY_ATTN_POLY=0|8|4 override.
     { const char* e = getenv("MICKEY_ATTN_PACK2"); pack = (e && e[0] == '0') ? 0 : 1; }
     // default: every 4th pair (25 %) on the FMA pipe -- measured 32.0 -> 29.9 us (one 720x540 pair) and 1156 -> 1100 us
     // (64 images, ViT-B); 12.5 % gives half of that, 50 % is slower than none (issue-bound).  MICKEY_ATTN_POLY=0 disables.
-    const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : (pack ? 8 : 4);
+    const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : 4;
   }
   CUtensorMap tm;
   int rc = make_tensor_map_f16(&tm, qkv, (long long)n_img * T, 3LL * D, 3LL * D, FA_BQ);

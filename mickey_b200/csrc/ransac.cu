@@ -97,10 +97,10 @@ __device__ __forceinline__ void for_each_cell(const CellView& cv, long long chun
     int rem[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long sidx = e0 / 4 + threadIdx.x + SAMP_THREADS * i;
+      const unsigned sidx = (unsigned)(e0 / 4) + threadIdx.x + SAMP_THREADS * i;      // N * spr < 2^31: 32-bit division
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f); e[i] = 0; rem[i] = 0;
-      if (sidx < slots) {
-        const int row = (int)(sidx / spr), c4 = (int)(sidx - (long long)row * spr) * 4;
+      if (sidx < (unsigned)slots) {
+        const int row = (int)(sidx / (unsigned)spr), c4 = (int)(sidx - (unsigned)row * (unsigned)spr) * 4;
         v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + (long long)row * cv.pitch + c4));
         e[i] = (long long)row * cv.N + c4;
         rem[i] = cv.N - c4;                                          // valid cells in this slot (>= 4 except at the row end)
@@ -300,9 +300,9 @@ sampler_collect_kernel(const float* __restrict__ fs, int N, long long pitch, int
           const long long e = e0 + 4LL * (threadIdx.x + SAMP_THREADS * i);
           if (e < cells) { v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + e)); eb[i] = e; rem[i] = 4; }
         } else {
-          const long long sidx = e0 / 4 + threadIdx.x + SAMP_THREADS * i;
-          if (sidx < slots) {
-            const int row = (int)(sidx / spr), c4 = (int)(sidx - (long long)row * spr) * 4;
+          const unsigned sidx = (unsigned)(e0 / 4) + threadIdx.x + SAMP_THREADS * i;     // N * spr < 2^31: 32-bit division
+          if (sidx < (unsigned)slots) {
+            const int row = (int)(sidx / (unsigned)spr), c4 = (int)(sidx - (unsigned)row * (unsigned)spr) * 4;
             v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + (long long)row * pitch + c4));
             eb[i] = (long long)row * N + c4; rem[i] = N - c4;
           }

@@ -122,3 +122,6 @@ idx = torch.zeros(8, 2048, dtype=torch.int32, device=dev)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 report("solve.sample_outer (8 streams)", timeit(lambda: _lib.check(lib.mk_op_sample(_lib.ptr(p), 1, N, 0, 8, 2048, 77, _lib.ptr(ws), nb, _lib.ptr(idx), _lib.ptr(status), stream())), iters=20),
        nbytes=N * N * 4)
+pp = (torch.rand(1, N, PITCH, device=dev) * 1e-9)
+report("solve.sample_outer (8 streams, row pitch 1952)", timeit(lambda: _lib.check(lib.mk_op_sample(_lib.ptr(pp), 1, N, PITCH, 8, 2048, 77, _lib.ptr(ws), nb, _lib.ptr(idx), _lib.ptr(status), stream())), iters=20),
+       nbytes=N * N * 4)
