@@ -39,6 +39,8 @@ from mickey_b200.weights import synthetic_checkpoint, synthetic_state_dict  # no
 H_IMG, W_IMG = 720, 540
 WORKLOADS = {
     # name: (variant, it_matches, it_ransac, pairs per GPU per step, description)
+    "c1": ("vitl", 20, 100, 1, "BASELINE configs[0] model on a synthetic pair: single 720x540 pair, ViT-L/14 (the reference's default backbone), 2000 hypotheses (20x100); "
+                               "the reference-CPU number of configs[0] itself (its toy_example JPEGs) is in profiles/r02_c1_reference_cpu.json"),
     "c2": ("vits", 8, 64, 1, "BASELINE configs[1]: single 720x540 synthetic pair, ViT-S/14, 512 hypotheses (8x64), 2048 sampled matches"),
     "c3": ("vitb", 16, 64, 32, "BASELINE configs[2]: batch of 32 synthetic 720x540 pairs, ViT-B/14, dual-softmax matcher, 1024 hypotheses (16x64), 2048 sampled matches"),
 }
@@ -448,6 +450,8 @@ def main():
 
     depth = args.depth or (1 if args.workload == "c3" else 3)
     n_blocks = args.blocks or (5 if args.workload == "c3" else 9)
+    if args.workload == "c1":
+        args.steps = min(args.steps, 20)
     m = measure(wl, depth, n_blocks)
     c2 = None
     if args.workload == "c3" and world == 1 and not args.no_c2:

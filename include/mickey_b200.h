@@ -101,7 +101,8 @@ int mk_match(mk_handle* h, int n_pairs, float* scores_dev, float* kp_scores_dev,
  * inlier_mask_dev fp32 [n_pairs, NUM_SAMPLED] (hard inliers of the winning set at the final pose),
  * sampled_idx_out_dev int32 [n_pairs*IT_MATCHES, NUM_SAMPLED] (the cells that were drawn),
  * hyp_scores_out_dev fp32 [n_pairs, IT_MATCHES*IT_RANSAC].  status_dev int32[1]: bit0 = not enough non-zero
- * cells, bit1 = candidate overflow, bit2 = non-finite hypothesis (bits 0/2 give the reference's zero pose). */
+ * cells, bit1 = candidate overflow (selection truncated), bit2 = non-finite hypothesis; any bit gives the reference's
+ * zero pose (R = 0, t = 0, inliers = 0 for the whole batch, probabilisticProcrustes.py:331-342). */
 int mk_solve_pose(mk_handle* h, const float* final_scores_dev, long long nn_pitch, const float* kps_dev, const float* depth_dev,
                   const float* K0_dev, const float* K1_dev, int n_pairs, int n_kpts, unsigned long long seed,
                   const int* outer_idx_dev, const int* inner_idx_dev, float* pose_dev, int* best_set_dev,

@@ -68,10 +68,24 @@ struct CellView {
   int N;
   long long pitch;
   __device__ __forceinline__ long long cells() const { return (long long)N * N; }
-  __device__ __forceinline__ long long work_items(int mode) const {       // what a block chunk is counted in
-    return mode == MODE_ROW_VEC ? (long long)N * ((N + 3) / 4) * 4 : cells();
+  // ROW_VEC: a block chunk is `rows_per_chunk` whole rows (no division in the cell loop); rows longer than a chunk
+  // (N > 4096) are not vectorised (the host picks MODE_SCALAR)
+  __device__ __forceinline__ int spr() const { return (N + 3) / 4; }                       // 4-cell slots per row
+  __device__ __forceinline__ int rows_per_chunk() const { return (SAMP_ELEMS_PER_BLOCK / 4) / spr(); }
+  __device__ __forceinline__ long long n_chunks(int mode) const {
+    if (mode == MODE_ROW_VEC) { const int rpc = rows_per_chunk(); return (N + rpc - 1) / rpc; }
+    return (cells() + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
   }
 };
+
+// slot `sl` of chunk `chunk` in ROW_VEC mode -> (row, first column); false beyond the chunk's rows / the matrix
+__device__ __forceinline__ bool row_vec_slot(const CellView& cv, long long chunk, int sl, int& row, int& c4) {
+  const int spr = cv.spr(), rpc = cv.rows_per_chunk();
+  int rr = 0;
+  while (sl >= spr && rr < rpc) { sl -= spr; ++rr; }                                        // rpc is 2 for N = 1938
+  row = (int)chunk * rpc + rr; c4 = sl * 4;
+  return rr < rpc && row < cv.N;
+}
 
 template <int MODE, typename F>
 __device__ __forceinline__ void for_each_cell(const CellView& cv, long long chunk, F&& f) {
@@ -90,17 +104,14 @@ __device__ __forceinline__ void for_each_cell(const CellView& cv, long long chun
       f(e[i], v[i].x); f(e[i] + 1, v[i].y); f(e[i] + 2, v[i].z); f(e[i] + 3, v[i].w);
     }
   } else if (MODE == MODE_ROW_VEC) {
-    const int spr = (cv.N + 3) / 4;                                  // 4-cell slots per row
-    const long long slots = (long long)cv.N * spr;
     float4 v[4];
     long long e[4];
     int rem[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const unsigned sidx = (unsigned)(e0 / 4) + threadIdx.x + SAMP_THREADS * i;      // N * spr < 2^31: 32-bit division
+      int row, c4;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f); e[i] = 0; rem[i] = 0;
-      if (sidx < (unsigned)slots) {
-        const int row = (int)(sidx / (unsigned)spr), c4 = (int)(sidx - (unsigned)row * (unsigned)spr) * 4;
+      if (row_vec_slot(cv, chunk, threadIdx.x + SAMP_THREADS * i, row, c4)) {
         v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + (long long)row * cv.pitch + c4));
         e[i] = (long long)row * cv.N + c4;
         rem[i] = cv.N - c4;                                          // valid cells in this slot (>= 4 except at the row end)
@@ -131,7 +142,7 @@ sampler_phist_kernel(const float* __restrict__ fs, int N, long long pitch, unsig
   __syncthreads();
   const int b = blockIdx.y;
   const CellView cv{fs + (long long)b * N * pitch, N, pitch};
-  const long long n_chunks = (cv.work_items(MODE) + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
+  const long long n_chunks = cv.n_chunks(MODE);
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)      // grid = whole waves of resident blocks
     for_each_cell<MODE>(cv, chunk, [&](long long, float pv) {
       if (pv > 0.f) atomicAdd(&h[__float_as_uint(pv) >> 20], 1u);
@@ -282,14 +293,13 @@ sampler_collect_kernel(const float* __restrict__ fs, int N, long long pitch, int
       if (any) collect_refine(rng, e, pv, uth, pth, r, sg, b, IM, T, cand, cnt, cap);
     }
   };
-  const long long n_chunks = (cv.work_items(MODE) + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
+  const long long n_chunks = cv.n_chunks(MODE);
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {    // grid = whole waves of resident blocks
     if (MODE != MODE_SCALAR) {
       // the four 16-byte loads first, then component-major processing: the loop body holds four (not sixteen)
       // copies of cell()
       const long long e0 = chunk * SAMP_ELEMS_PER_BLOCK;
-      const int spr = (N + 3) / 4;
-      const long long cells = cv.cells(), slots = (long long)N * spr;
+      const long long cells = cv.cells();
       float4 v[4];
       long long eb[4];
       int rem[4];
@@ -300,9 +310,8 @@ sampler_collect_kernel(const float* __restrict__ fs, int N, long long pitch, int
           const long long e = e0 + 4LL * (threadIdx.x + SAMP_THREADS * i);
           if (e < cells) { v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + e)); eb[i] = e; rem[i] = 4; }
         } else {
-          const unsigned sidx = (unsigned)(e0 / 4) + threadIdx.x + SAMP_THREADS * i;     // N * spr < 2^31: 32-bit division
-          if (sidx < (unsigned)slots) {
-            const int row = (int)(sidx / (unsigned)spr), c4 = (int)(sidx - (unsigned)row * (unsigned)spr) * 4;
+          int row, c4;
+          if (row_vec_slot(cv, chunk, threadIdx.x + SAMP_THREADS * i, row, c4)) {
             v[i] = __ldg(reinterpret_cast<const float4*>(cv.p + (long long)row * pitch + c4));
             eb[i] = (long long)row * N + c4; rem[i] = N - c4;
           }
@@ -312,8 +321,11 @@ sampler_collect_kernel(const float* __restrict__ fs, int N, long long pitch, int
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float pv = (c == 0) ? v[i].x : (c == 1) ? v[i].y : (c == 2) ? v[i].z : v[i].w;
-          if (MODE == MODE_FLAT_VEC || rem[i] > c) cell(eb[i] + c, pv);      // flat mode: out-of-range slots hold zeros
+          // cells beyond the row end are fed as probability 0 (a select, not a branch: the four Philox evaluations of
+          // this step stay interleaved); flat mode: out-of-range slots already hold zeros
+          float pv = (c == 0) ? v[i].x : (c == 1) ? v[i].y : (c == 2) ? v[i].z : v[i].w;
+          if (MODE != MODE_FLAT_VEC) pv = (rem[i] > c) ? pv : 0.f;
+          cell(eb[i] + c, pv);
         }
       }
     } else {
@@ -488,9 +500,11 @@ int sample_outer(const float* final_scores, int B, int N, long long pitch, int I
   // one block per 4096-cell chunk (the hardware block scheduler balances the 1.5 waves at chunk granularity); the
   // kernels loop over chunks so that a smaller grid stays correct
   const bool aligned = reinterpret_cast<uintptr_t>(final_scores) % 16 == 0;
-  const int mode = (pitch == N && cells % 4 == 0 && aligned) ? MODE_FLAT_VEC : (pitch % 4 == 0 && aligned) ? MODE_ROW_VEC : MODE_SCALAR;
-  const long long items = (mode == MODE_ROW_VEC) ? (long long)N * ((N + 3) / 4) * 4 : cells;
-  dim3 grid((unsigned)min((items + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK, 65535LL * 16), B);
+  const int spr = (N + 3) / 4, rpc = (SAMP_ELEMS_PER_BLOCK / 4) / spr;              // ROW_VEC: whole rows per block chunk
+  const int mode = (pitch == N && cells % 4 == 0 && aligned) ? MODE_FLAT_VEC
+                   : (pitch % 4 == 0 && pitch >= 4LL * spr && aligned && rpc >= 1) ? MODE_ROW_VEC : MODE_SCALAR;
+  const long long chunks = (mode == MODE_ROW_VEC) ? (N + rpc - 1) / rpc : (cells + SAMP_ELEMS_PER_BLOCK - 1) / SAMP_ELEMS_PER_BLOCK;
+  dim3 grid((unsigned)min(chunks, 65535LL * 16), B);
   if (mode == MODE_FLAT_VEC) sampler_phist_kernel<MODE_FLAT_VEC><<<grid, SAMP_THREADS, 0, st>>>(final_scores, N, pitch, hist);
   else if (mode == MODE_ROW_VEC) sampler_phist_kernel<MODE_ROW_VEC><<<grid, SAMP_THREADS, 0, st>>>(final_scores, N, pitch, hist);
   else sampler_phist_kernel<MODE_SCALAR><<<grid, SAMP_THREADS, 0, st>>>(final_scores, N, pitch, hist);
@@ -880,7 +894,9 @@ ransac_finalize_kernel(const float* __restrict__ xyw, const float* __restrict__ 
   }
   block_reduce_sum(acc, 1, scratch);
   if (tid == 0) {
-    const bool invalid = (*status & (1 | 4)) != 0;       // batch-level zero fallback (:261-262,329-342)
+    // batch-level zero fallback (:261-262,329-342): too few non-zero cells (1), a non-finite hypothesis (4), and -- never
+    // silently -- a truncated candidate list (2; probability < 1e-13 by the threshold's construction)
+    const bool invalid = (*status & (1 | 2 | 4)) != 0;
     float* o = pose + (long long)b * 13;
     for (int i = 0; i < 9; ++i) o[i] = invalid ? 0.f : Rs[i];
     for (int i = 0; i < 3; ++i) o[9 + i] = invalid ? 0.f : ts[i];

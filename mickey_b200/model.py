@@ -95,7 +95,7 @@ class e2eProbabilisticProcrustesSolver:
         w = final[bidx, i0, i1]
         rows = torch.cat([batch["kps0"][bidx, :, i0], batch["kps1"][bidx, :, i1], w[..., None],
                           batch["depth_kp0"][bidx, :, i0], batch["depth_kp1"][bidx, :, i1]], dim=-1)
-        zero_pose = bool((res["status"].item() & 5) != 0)
+        zero_pose = bool((res["status"].item() & 7) != 0)
         out = []
         for b in range(B):
             if zero_pose:
@@ -254,7 +254,7 @@ class MickeyRelativePose(nn.Module):
         w = data["final_scores"][bidx, i0, i1]
         rows = torch.cat([data["kps0"][bidx, :, i0], data["kps1"][bidx, :, i1], w[..., None],
                           data["depth_kp0"][bidx, :, i0], data["depth_kp1"][bidx, :, i1]], dim=-1)
-        if int(st["status"].item()) & 5:
+        if int(st["status"].item()) & 7:
             return [torch.zeros([0, 5])] * B
         out = []
         for b in range(B):
