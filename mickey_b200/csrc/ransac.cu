@@ -264,7 +264,7 @@ __device__ __noinline__ void collect_refine(const Philox& rng, long long e, floa
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(SAMP_THREADS)
+__global__ void __launch_bounds__(SAMP_THREADS, 3)       // three blocks per SM (<= 85 registers): the pitched mode compiled to 104 without the cap
 sampler_collect_kernel(const float* __restrict__ fs, int N, long long pitch, int IM, const unsigned long long* __restrict__ seed_ptr,
                        const int* __restrict__ thr, const float* __restrict__ inv_tau_p, unsigned long long* __restrict__ cand,
                        unsigned int* __restrict__ cnt, int cap) {

@@ -69,6 +69,17 @@ def gather_poses(packed: torch.Tensor, n_pairs: int = None) -> torch.Tensor:
     return torch.cat(keep, dim=0)
 
 
+def step_plan(n_pairs: int, world_size: int, batch_size: int):
+    """For a pair list sharded contiguously by rank (shard_range) and consumed in batches of `batch_size`: the number of
+    steps every rank has to join (the longest shard decides) and, per step, how many real rows each rank contributes to
+    the step's one all-gather (0 once its shard is exhausted).  Every rank computes the same plan, so the collective
+    count matches without any extra communication (tools/run_submission.py)."""
+    shard_len = [e - s for s, e in (shard_range(n_pairs, r, world_size) for r in range(world_size))]
+    n_steps = max(-(-l // batch_size) for l in shard_len) if n_pairs > 0 else 0
+    rows = [[max(0, min(batch_size, l - step * batch_size)) for l in shard_len] for step in range(n_steps)]
+    return n_steps, rows
+
+
 def forward_sharded(model, data: dict, return_inliers: bool = False):
     """Run `model` on this rank's shard of a global batch and return the globally gathered (R, t, inliers)."""
     local = shard_batch(data)

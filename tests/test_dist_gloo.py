@@ -72,3 +72,18 @@ def test_two_rank_gloo_gather_matches_single_process(tmp_path, n_pairs):
     data = {"image0": torch.arange(n_pairs, dtype=torch.float32).view(n_pairs, 1, 1, 1).repeat(1, 3, 2, 2)}
     R, t = _FakeModel()(data)
     assert torch.equal(got["R"], R) and torch.equal(got["t"], t) and torch.equal(got["inl"], data["inliers"])
+
+
+def test_step_plan_covers_every_pair_once():
+    """The per-step row counts of the sharded submission run: every pair appears exactly once, in rank order per step,
+    and all ranks agree on the number of collectives."""
+    from mickey_b200.dist import shard_range, step_plan
+    for n_pairs, world, bs in [(192, 8, 12), (5, 2, 12), (64, 2, 12), (7, 8, 4), (0, 4, 8), (100, 3, 7)]:
+        n_steps, rows = step_plan(n_pairs, world, bs)
+        assert len(rows) == n_steps and all(len(r) == world for r in rows)
+        per_rank = [sum(r[k] for r in rows) for k in range(world)]
+        assert per_rank == [e - s for s, e in (shard_range(n_pairs, k, world) for k in range(world))]
+        assert sum(per_rank) == n_pairs and all(0 <= x <= bs for r in rows for x in r)
+        for k in range(world):                      # a rank's rows are consumed front to back: no gaps
+            col = [r[k] for r in rows]
+            assert all(col[i] == bs or sum(col[i + 1:]) == 0 for i in range(len(col)))

@@ -79,8 +79,7 @@ def main():
     dm = DataModule(cfg, drop_last_val=False, uint8_images=args.uint8, pin_memory=True)
     loader = dm.val_dataloader() if args.split == "val" else dm.test_dataloader()
     n_pairs = len(loader.dataset)
-    shard_len = [e - s for s, e in (mkdist.shard_range(n_pairs, r, world) for r in range(world))]
-    n_steps = max(-(-l // BS) for l in shard_len)
+    n_steps, step_rows = mkdist.step_plan(n_pairs, world, BS)
     ckpt = synthetic_checkpoint(cfg, seed=0, with_backbone=True) if args.checkpoint == "synthetic" else args.checkpoint
     model = build_model(cfg, ckpt)
 
@@ -99,7 +98,7 @@ def main():
     t0 = time.perf_counter()
     it = iter(loader)
     for step in range(n_steps):
-        rows = [max(0, min(BS, l - step * BS)) for l in shard_len]
+        rows = step_rows[step]
         mine = torch.zeros(BS, 13, device=dev)
         if rows[rank] > 0:
             data = next(it)
