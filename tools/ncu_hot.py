@@ -28,7 +28,16 @@ def col(name):
 c_src, c_samp, c_exec, c_line = col("Source"), col("Warp Stall Sampling (All"), col("Instructions Executed"), col("# Line") or col("Address")
 body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
 tot = sum(float(r[c_samp] or 0) for r in body) or 1.0
-print(f"kernel filter '{want}': {len(body)} SASS instructions, {tot:.0f} stall samples; columns: {[h for h in hdr][:12]}")
+print(f"kernel filter '{want}': {len(body)} SASS instructions, {tot:.0f} stall samples")
+print("columns:", hdr)
+# cumulative share by SASS opcode
+from collections import Counter
+by_op = Counter()
+for r in body:
+    toks = r[c_src].split()
+    op = (toks[1] if toks and toks[0].startswith("@") and len(toks) > 1 else (toks[0] if toks else "?")).split(".")[0]
+    by_op[op] += float(r[c_samp] or 0)
+print("stall samples by opcode:", ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in by_op.most_common(25)))
 body.sort(key=lambda r: -float(r[c_samp] or 0))
 for r in body[:top]:
     print(f"{100 * float(r[c_samp] or 0) / tot:6.2f}%  exec={r[c_exec]:>10s}  {r[c_src][:110]}")
