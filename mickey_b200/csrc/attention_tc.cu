@@ -92,6 +92,37 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
   asm("{\n\t.reg .b64 ra, rd;\n\tmov.b64 rd, {%0, %1};\n\tmov.b64 ra, {%2, %3};\n\tadd.rn.f32x2 rd, rd, ra;\n\tmov.b64 {%0, %1}, rd;\n\t}"
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
+// pair * pair + broadcast, pair * broadcast + pair, pair + broadcast: the FMA-pipe exp2 on two logits per instruction
+__device__ __forceinline__ void fma2_ppb(float& d0, float& d1, float a0, float a1, float b0, float b1, float c) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c));
+}
+__device__ __forceinline__ void fma2_pbp(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2_pb(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b));
+}
+// exp2_fma on a pair of logits: the same operations in the same order (fma.rn.f32x2 / add.rn.f32x2 round each half like
+// the scalar instruction), 11 issue slots per pair instead of 18.
+__device__ __forceinline__ void exp2_fma_pair(float& p0, float& p1, float x0, float x1) {
+  x0 = fmaxf(x0, -125.0f); x1 = fmaxf(x1, -125.0f);
+  float t0, t1, u0, u1, f0, f1;
+  add2_pb(t0, t1, x0, x1, 12582912.0f);
+  add2_pb(u0, u1, t0, t1, -12582912.0f);
+  fma2_pbp(f0, f1, u0, u1, -1.0f, x0, x1);         // x - u, exact product: identical to the subtraction
+  fma2_pbp(p0, p1, f0, f1, 0.0096181291f, 0.0555041087f, 0.0555041087f);
+  fma2_ppb(p0, p1, p0, p1, f0, f1, 0.2402265070f);
+  fma2_ppb(p0, p1, p0, p1, f0, f1, 0.6931471806f);
+  fma2_ppb(p0, p1, p0, p1, f0, f1, 1.0f);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -116,7 +147,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <int POLY, int PK>     // every POLY-th pair of logits takes the FMA-pipe exp2 (0: none); PK: packed fp32x2 scale / row sum
+template <int POLY, int PK>     // every POLY-th pair of logits takes the FMA-pipe exp2 (0: none); PK >= 1: packed fp32x2 scale / row sum, 2: and polynomial
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int D, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -267,7 +298,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
         if (PK) fma2(x0, x1, s[2 * i], s[2 * i + 1], scale_log2, neg_m);
         else { x0 = fmaf(s[2 * i], scale_log2, neg_m); x1 = fmaf(s[2 * i + 1], scale_log2, neg_m); }
         const bool poly = (POLY > 0) && (i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1);
-        const float p0 = poly ? exp2_fma(x0) : ex2_approx(x0), p1 = poly ? exp2_fma(x1) : ex2_approx(x1);
+        float p0, p1;
+        if (poly && PK == 2) exp2_fma_pair(p0, p1, x0, x1);
+        else { p0 = poly ? exp2_fma(x0) : ex2_approx(x0); p1 = poly ? exp2_fma(x1) : ex2_approx(x1); }
         if (PK) { if (i & 1) add2(sa[2], sa[3], p0, p1); else add2(sa[0], sa[1], p0, p1); }
         else { sa[(2 * i) & 3] += p0; sa[(2 * i + 1) & 3] += p1; }
         __half2 h = __floats2half2_rn(p0, p1);
@@ -341,17 +374,18 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   static unsigned long long attr_mask = 0;
   static int poly = 0, pack = 0;
   if (first_use_on_device(attr_mask)) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    const void* all[] = {(const void*)attention_tc_kernel<0, 0>, (const void*)attention_tc_kernel<8, 0>, (const void*)attention_tc_kernel<4, 0>,
+                         (const void*)attention_tc_kernel<0, 1>, (const void*)attention_tc_kernel<8, 1>, (const void*)attention_tc_kernel<4, 1>,
+                         (const void*)attention_tc_kernel<8, 2>, (const void*)attention_tc_kernel<4, 2>};
+    for (const void* f : all) MK_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     // packed fp32x2 scale / row sum (FFMA2 / FADD2): on by default (64 images, ViT-B: 1113 -> 1081 us with every 4th pair on
     // the FMA-pipe exp2, 1058 us with every 8th).  Every 4th stays the default: the `scores` parity metric, which amplifies
     // the features' error through logits of +-10, was consistently better with it (ViT-L 720x540: 7.9e-4 vs 1.03e-3 for
     // every 8th and 8.6e-4 for none; profiles/r02_notes.md).  MICKEY_ATTN_PACK2=0 / MICKEY_ATTN_POLY=0|8|4 override.
-    { const char* e = getenv("MICKEY_ATTN_PACK2"); pack = (e && e[0] == '0') ? 0 : 1; }
+    // MICKEY_ATTN_PACK2=2 (default) also evaluates the polynomial on packed pairs: 61 fewer instructions per 64 logits, the
+    // same results bit for bit, and the same time (64 images: 1073 vs 1074 us, session 14) -- with every 3rd pair on the
+    // polynomial 1052 us, every 2nd 1178 us, every 8th 1117 us: neither the issue slots nor the FMA pipe alone bound the loop.
+    { const char* e = getenv("MICKEY_ATTN_PACK2"); pack = e ? atoi(e) : 2; if (pack < 0 || pack > 2) pack = 2; }
     // default: every 4th pair (25 %) on the FMA pipe -- measured 32.0 -> 29.9 us (one 720x540 pair) and 1156 -> 1100 us
     // (64 images, ViT-B); 12.5 % gives half of that, 50 % is slower than none (issue-bound).  MICKEY_ATTN_POLY=0 disables.
     const char* e = getenv("MICKEY_ATTN_POLY"); poly = e ? atoi(e) : 4;
@@ -361,8 +395,9 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   if (rc) return rc;
   dim3 grid(ceil_div(T, FA_BQ), heads, n_img);
   const float scale_log2 = 0.125f * 1.4426950408889634f;
-  auto kern = pack ? (poly == 8 ? attention_tc_kernel<8, 1> : poly == 4 ? attention_tc_kernel<4, 1> : attention_tc_kernel<0, 1>)
-                   : (poly == 8 ? attention_tc_kernel<8, 0> : poly == 4 ? attention_tc_kernel<4, 0> : attention_tc_kernel<0, 0>);
+  auto kern = pack == 2 ? (poly == 8 ? attention_tc_kernel<8, 2> : poly == 4 ? attention_tc_kernel<4, 2> : attention_tc_kernel<0, 1>)
+            : pack == 1 ? (poly == 8 ? attention_tc_kernel<8, 1> : poly == 4 ? attention_tc_kernel<4, 1> : attention_tc_kernel<0, 1>)
+                        : (poly == 8 ? attention_tc_kernel<8, 0> : poly == 4 ? attention_tc_kernel<4, 0> : attention_tc_kernel<0, 0>);
   MK_CUDA_CHECK(launch_k(kern, grid, dim3(FA_THREADS), (size_t)FA_SMEM, s, tm, (__half*)out, T, D, scale_log2));
   return MK_OK;
 }

@@ -267,12 +267,21 @@ static bool two_sm_enabled() {
   return v != 0;
 }
 
-template <int EPI>
-static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+// ring depth of the cta_group::2 kernel: 4 stages + 64-column epilogue passes, or 5 stages + 32-column passes for long K
+// (gemm_tc.cuh; MICKEY_GEMM_2SM_STAGES=4|5 forces one)
+static int two_sm_stages_forced() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_2SM_STAGES"); const int n = e ? atoi(e) : 0; v = (n == 4 || n == 5) ? n : 0; }
+  return v;
+}
+
+template <int EPI, int STAGES>
+static int launch_2sm_s(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   static unsigned long long attr_mask = 0;
-  constexpr int smem = gemm_2sm_smem_bytes();
+  constexpr int smem = gemm_2sm_smem_bytes<STAGES>();
+  static_assert(smem <= 227 * 1024, "cta_group::2 kernel: shared memory");
   if (first_use_on_device(attr_mask)) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const long long total = (long long)tiles256.x * tiles256.y * tiles256.z;
   const long long pairs = sm_count() / 2;
@@ -286,8 +295,14 @@ static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI>, tmA, tmB, p, (int)tiles256.x, (int)tiles256.y, no_out_maps()));
+  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI, STAGES>, tmA, tmB, p, (int)tiles256.x, (int)tiles256.y, no_out_maps()));
   return MK_OK;
+}
+template <int EPI>
+static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  const int forced = two_sm_stages_forced();
+  const int st = forced ? forced : (p.k_chunks >= TWO_SM_LONG_K_CHUNKS ? 5 : 4);
+  return st == 5 ? launch_2sm_s<EPI, 5>(tiles256, tmA, tmB, p, stream) : launch_2sm_s<EPI, 4>(tiles256, tmA, tmB, p, stream);
 }
 
 static bool three_enabled() {

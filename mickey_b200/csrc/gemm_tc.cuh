@@ -151,7 +151,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t
 constexpr int DUAL_STAGE_BYTES = 3 * 4096;
 constexpr int DUAL_AUX_BYTES = 8 * 64 * 4;
 
-template <int BN, int EPI, typename Release>
+template <int BN, int EPI, int PWMAX = 64, typename Release>
 __device__ __forceinline__ void tile_epilogue(const GemmParams& p, const OutMaps& om, int g, int m0, int n0, int n_tile, int q, int half,
                                               int lane, uint32_t tmem_acc, float* stage, Release release,
                                               float* red = nullptr, uint32_t red_saddr = 0, float* dual_stage = nullptr,
@@ -275,8 +275,8 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, const OutMaps
     }
     release();
   } else {
-    // the warp's columns are processed in passes of at most 64 (two 32-column TMEM loads) through the staging block
-    constexpr int PW = (W > 64) ? 64 : W;                 // staged columns per pass
+    // the warp's columns are processed in passes of at most PWMAX (64: two 32-column TMEM loads) through the staging block
+    constexpr int PW = (W > PWMAX) ? PWMAX : W;           // staged columns per pass
     constexpr int PCH = PW / 32;                          // chunks per pass
     for (int c0 = c_begin; c0 < c_end; c0 += PCH) {
 #pragma unroll
@@ -573,9 +573,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 // complete_tx on it: peer bit of the mbarrier address cleared), `empty` / `tmem_full` are signalled in both CTAs by a
 // multicast tcgen05.commit, `tmem_empty` lives in the leader and collects the 8 epilogue warps of both CTAs (the peer
 // arrives remotely).  Warp roles as in the 1-SM persistent kernel; the peer's MMA warp idles.
-constexpr int TWO_SM_STAGES = 4;
-constexpr int gemm_2sm_smem_bytes() {
-  return TWO_SM_STAGES * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 8 * 32 * (64 + 4) * 4 + 1024 + 256;
+// Ring depth vs. epilogue staging (227 KB per CTA): 4 stages of 32 KB + 64-column staging passes (8 warps x 32 x 68 floats),
+// or 5 stages + 32-column passes (8 x 32 x 36 floats).  Measured (round 2, sessions 14/15, 64 images of ViT-B): the deeper
+// ring pays where K is long and the A operand streams from HBM (mlp.fc2, K = 3072: 464 -> 452 us; 16384 x 4096 x 4096:
+// 1526 -> 1546 TFLOP/s) and the shorter passes cost where K = 768 (qkv 338 -> 350, proj 224 -> 239, fc1 544 -> 560 us), so
+// the dispatcher takes 5 stages from 32 K chunks on.  A staging-free variant (thread == row, 256-bit stores straight from the
+// tcgen05.ld layout, 6-7 stages) was correct but slower everywhere K is short (proj 222 -> 263 us, qkv 343 -> 360 us): 32
+// different 128-byte lines per store instruction cost more than the shared-memory round trip they saved; it was removed.
+constexpr int TWO_SM_LONG_K_CHUNKS = 32;
+template <int TWO_SM_STAGES> constexpr int two_sm_pass_cols() { return TWO_SM_STAGES >= 5 ? 32 : 64; }
+template <int TWO_SM_STAGES> constexpr int two_sm_staging_bytes() { return 8 * 32 * (two_sm_pass_cols<TWO_SM_STAGES>() + 4) * 4; }
+template <int TWO_SM_STAGES> constexpr int gemm_2sm_smem_bytes() {
+  return TWO_SM_STAGES * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + two_sm_staging_bytes<TWO_SM_STAGES>() + 1024 + 256;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -609,7 +618,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int EPI>
+template <int EPI, int TWO_SM_STAGES>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmParams p, const int tiles_m, const int tiles_n, const __grid_constant__ OutMaps om) {
@@ -619,7 +628,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                    // this CTA's 128 rows of A
   constexpr int B_BYTES = 128 * BLOCK_K * 2;                        // this CTA's 128 rows (N half) of B
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGING_BYTES = 8 * 32 * (64 + 4) * 4;
+  constexpr int PASS_COLS = two_sm_pass_cols<TWO_SM_STAGES>();
+  constexpr int STAGING_BYTES = two_sm_staging_bytes<TWO_SM_STAGES>();
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   const uint32_t raw = smem_u32(smem_raw);
@@ -715,7 +725,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===== epilogue warps (both CTAs): this CTA's 128 rows x 256 columns =====
     const int ew = warp - 4;
     const int q = warp & 3, half = ew >> 2;
-    float* stage_buf = reinterpret_cast<float*>(smem_raw + (staging - raw)) + ew * (32 * (64 + 4));
+    float* stage_buf = reinterpret_cast<float*>(smem_raw + (staging - raw)) + ew * (32 * (PASS_COLS + 4));
     int it = 0;
     for (int t = cluster_id; t < total; t += n_clusters, ++it) {
       const int g = t / tiles_per_group, r = t - g * tiles_per_group;
@@ -725,7 +735,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(tfull_bar0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tb = tempty_bar0 + 8 * acc;
-      tile_epilogue<BN, EPI>(p, om, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
+      tile_epilogue<BN, EPI, PASS_COLS>(p, om, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tb, 0);                   // the leader's barrier (also from the leader itself)

@@ -219,6 +219,15 @@ def test_gemm_2sm():
     ref = x + gamma * (a.float() @ w.float().t() + bias)
     gemm("RESID_F", a, w, M, N, K, bias=bias, gamma=gamma, out_f=x, out_f_ld=N)
     assert rel_err(x, ref) < 1e-5
+    # fp32 store (head linear-attention q, k, v) and the plain fp16 store without bias; rows beyond M stay untouched
+    out_f = torch.full((M + 8, N), 7.0, device=DEV)
+    gemm("STORE_F", a, w, M, N, K, out_f=out_f, out_f_ld=N)
+    assert rel_err(out_f[:M], a.float() @ w.float().t()) < 1e-5
+    assert bool((out_f[M:] == 7.0).all())
+    out_h = torch.full((M + 8, N), 7.0, dtype=torch.float16, device=DEV)
+    gemm("STORE_H", a, w, M, N, K, out_h=out_h, out_h_ld=N)
+    assert rel_err(out_h[:M], a.float() @ w.float().t()) < 1e-3
+    assert bool((out_h[M:] == 7.0).all())
 
 
 def test_patch_gather_and_patch_epilogue():
