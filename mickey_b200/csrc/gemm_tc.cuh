@@ -615,7 +615,12 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, u
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // default semantics (release at CTA scope: no fence instruction).  `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR
+  // in front of the arrive, i.e. every epilogue warp waited for its in-flight global stores to be acknowledged before it
+  // handed each accumulator back (ncu: `stall membar` among the top stalls of the K = 768 GEMMs).  Nothing in generic memory
+  // is published through this barrier: it orders tcgen05.ld (completed by tcgen05.wait::ld + fence::before_thread_sync)
+  // against the leader's next tcgen05.mma into the same TMEM columns.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 template <int EPI, int TWO_SM_STAGES>
