@@ -275,18 +275,24 @@ static int two_sm_stages_forced() {
   return v;
 }
 
-template <int EPI, int STAGES>
+static int two_sm_epi_warps_forced() {      // MICKEY_GEMM_2SM_EPIWARPS=8|16 forces one; default: by epilogue (launch_2sm)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MICKEY_GEMM_2SM_EPIWARPS"); const int n = e ? atoi(e) : 0; v = (n == 8 || n == 16) ? n : 0; }
+  return v;
+}
+
+template <int EPI, int STAGES, int EPI_WARPS>
 static int launch_2sm_s(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   static unsigned long long attr_mask = 0;
-  constexpr int smem = gemm_2sm_smem_bytes<STAGES>();
+  constexpr int smem = gemm_2sm_smem_bytes<STAGES, EPI_WARPS>();
   static_assert(smem <= 227 * 1024, "cta_group::2 kernel: shared memory");
   if (first_use_on_device(attr_mask)) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI, STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const long long total = (long long)tiles256.x * tiles256.y * tiles256.z;
   const long long pairs = sm_count() / 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs))); cfg.blockDim = dim3(PERSIST_THREADS);
+  cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs))); cfg.blockDim = dim3(128 + 32 * EPI_WARPS);
   cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -295,14 +301,23 @@ static int launch_2sm_s(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI, STAGES>, tmA, tmB, p, (int)tiles256.x, (int)tiles256.y, no_out_maps()));
+  MK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI, STAGES, EPI_WARPS>, tmA, tmB, p, (int)tiles256.x, (int)tiles256.y, no_out_maps()));
   return MK_OK;
 }
 template <int EPI>
 static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   const int forced = two_sm_stages_forced();
   const int st = forced ? forced : (p.k_chunks >= TWO_SM_LONG_K_CHUNKS ? 5 : 4);
-  return st == 5 ? launch_2sm_s<EPI, 5>(tiles256, tmA, tmB, p, stream) : launch_2sm_s<EPI, 4>(tiles256, tmA, tmB, p, stream);
+  if constexpr (EPI == EPI_STORE_H || EPI == EPI_RESID_F || EPI == EPI_STORE_F) {
+    // Short K: a heavy epilogue needs more issue slots than two warps per sub-partition give.  16 epilogue warps (four per
+    // TMEM lane quadrant, 32-column passes) measured against 8 on 64 images of ViT-B: mlp.fc1 + GELU 546 -> 516 us alone,
+    // 7.29 -> 6.42 ms in the C3 step; attn.proj (fp32 read-modify-write) 218 -> 204 us, 2.96 -> 2.63 ms; the plain fp16
+    // store of attn.qkv loses 1 % to the shorter passes and keeps 8.
+    const int forced_w = two_sm_epi_warps_forced();
+    const bool heavy = (EPI == EPI_RESID_F) || (EPI == EPI_STORE_H && p.act != ACT_NONE);
+    if (st == 4 && (forced_w ? forced_w == 16 : heavy)) return launch_2sm_s<EPI, 4, 16>(tiles256, tmA, tmB, p, stream);
+  }
+  return st == 5 ? launch_2sm_s<EPI, 5, 8>(tiles256, tmA, tmB, p, stream) : launch_2sm_s<EPI, 4, 8>(tiles256, tmA, tmB, p, stream);
 }
 
 static bool three_enabled() {

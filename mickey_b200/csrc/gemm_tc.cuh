@@ -151,14 +151,17 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t
 constexpr int DUAL_STAGE_BYTES = 3 * 4096;
 constexpr int DUAL_AUX_BYTES = 8 * 64 * 4;
 
-template <int BN, int EPI, int PWMAX = 64, typename Release>
+template <int BN, int EPI, int PWMAX = 64, int NPARTS = 2, typename Release>
 __device__ __forceinline__ void tile_epilogue(const GemmParams& p, const OutMaps& om, int g, int m0, int n0, int n_tile, int q, int half,
                                               int lane, uint32_t tmem_acc, float* stage, Release release,
                                               float* red = nullptr, uint32_t red_saddr = 0, float* dual_stage = nullptr,
                                               float* dual_aux = nullptr) {
+  // NPARTS warps share a TMEM lane quadrant and split the tile's columns (`half` = this warp's part, 0..NPARTS-1)
+  static_assert(NPARTS == 2 || (NPARTS == 4 && BN == 256 && (EPI == EPI_STORE_H || EPI == EPI_RESID_F || EPI == EPI_STORE_F)),
+                "4 column parts: 256-wide tiles, plain store / residual epilogues");
   constexpr int CHUNKS = BN / 32;
-  constexpr int CPH = (CHUNKS + 1) / 2;          // chunks per half
-  constexpr int W = BN / 2;                      // columns owned by this warp
+  constexpr int CPH = (CHUNKS + NPARTS - 1) / NPARTS;   // chunks per part
+  constexpr int W = BN / NPARTS;                        // columns owned by this warp
   const int c_begin = half * CPH;
   const int c_end = (c_begin + CPH < CHUNKS) ? c_begin + CPH : CHUNKS;
   const int m = m0 + q * 32 + lane;
@@ -581,10 +584,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 // tcgen05.ld layout, 6-7 stages) was correct but slower everywhere K is short (proj 222 -> 263 us, qkv 343 -> 360 us): 32
 // different 128-byte lines per store instruction cost more than the shared-memory round trip they saved; it was removed.
 constexpr int TWO_SM_LONG_K_CHUNKS = 32;
-template <int TWO_SM_STAGES> constexpr int two_sm_pass_cols() { return TWO_SM_STAGES >= 5 ? 32 : 64; }
-template <int TWO_SM_STAGES> constexpr int two_sm_staging_bytes() { return 8 * 32 * (two_sm_pass_cols<TWO_SM_STAGES>() + 4) * 4; }
-template <int TWO_SM_STAGES> constexpr int gemm_2sm_smem_bytes() {
-  return TWO_SM_STAGES * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + two_sm_staging_bytes<TWO_SM_STAGES>() + 1024 + 256;
+// EPI_WARPS = 16 (four warps per TMEM lane quadrant, 64 columns each, 640 threads): twice the issue capacity for the
+// epilogue; 32-column passes so that 16 staging blocks fit next to a 4-stage ring.
+template <int TWO_SM_STAGES, int EPI_WARPS> constexpr int two_sm_pass_cols() { return (TWO_SM_STAGES >= 5 || EPI_WARPS > 8) ? 32 : 64; }
+template <int TWO_SM_STAGES, int EPI_WARPS> constexpr int two_sm_staging_bytes() {
+  return EPI_WARPS * 32 * (two_sm_pass_cols<TWO_SM_STAGES, EPI_WARPS>() + 4) * 4;
+}
+template <int TWO_SM_STAGES, int EPI_WARPS = 8> constexpr int gemm_2sm_smem_bytes() {
+  return TWO_SM_STAGES * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + two_sm_staging_bytes<TWO_SM_STAGES, EPI_WARPS>() + 1024 + 256;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -623,8 +630,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int EPI, int TWO_SM_STAGES>
-__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+template <int EPI, int TWO_SM_STAGES, int EPI_WARPS = 8>
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmParams p, const int tiles_m, const int tiles_n, const __grid_constant__ OutMaps om) {
   // tiles_m = ceil(M / 256), tiles_n = N / 256; cluster c = blockIdx.x / 2 walks tiles c, c + gridDim.x / 2, ...
@@ -633,8 +640,9 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                    // this CTA's 128 rows of A
   constexpr int B_BYTES = 128 * BLOCK_K * 2;                        // this CTA's 128 rows (N half) of B
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int PASS_COLS = two_sm_pass_cols<TWO_SM_STAGES>();
-  constexpr int STAGING_BYTES = two_sm_staging_bytes<TWO_SM_STAGES>();
+  constexpr int PASS_COLS = two_sm_pass_cols<TWO_SM_STAGES, EPI_WARPS>();
+  constexpr int STAGING_BYTES = two_sm_staging_bytes<TWO_SM_STAGES, EPI_WARPS>();
+  constexpr int NPARTS = EPI_WARPS / 4;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   const uint32_t raw = smem_u32(smem_raw);
@@ -661,7 +669,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TWO_SM_STAGES; ++s) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar0 + 8 * a, 1); mbar_init(tempty_bar0 + 8 * a, 16); }   // 8 warps x 2 CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar0 + 8 * a, 1); mbar_init(tempty_bar0 + 8 * a, 2 * EPI_WARPS); }   // epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {     // both CTAs, same warp id, same destination offset
@@ -740,7 +748,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(tfull_bar0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tb = tempty_bar0 + 8 * acc;
-      tile_epilogue<BN, EPI, PASS_COLS>(p, om, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
+      tile_epilogue<BN, EPI, PASS_COLS, NPARTS>(p, om, g, m0, n0, n_tile, q, half, lane, tmem_base + acc * BN, stage_buf, [&] {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tb, 0);                   // the leader's barrier (also from the leader itself)
