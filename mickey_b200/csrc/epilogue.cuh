@@ -24,6 +24,41 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, copysignf(erf_abs, x), hx);
 }
 
+// The same function on two values with packed fp32x2 arithmetic (FFMA2 / FMUL2: one issue slot for both halves, each half
+// rounded like the scalar instruction): the same operations in the same order as gelu_erf, hence the same bits; the
+// polynomial is carried negated (RN is symmetric) so that no separate negation is needed.  22 issue slots per pair instead
+// of 34: the GELU epilogue of mlp.fc1 is bound by instruction issue (profiles/r02_notes.md).
+#define MK_F32X2_OP3(name, ptx)                                                                                      \
+  __device__ __forceinline__ void name(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) { \
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"  \
+        ptx " rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"                                                        \
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));                                 \
+  }
+MK_F32X2_OP3(fma2_f32, "fma.rn.f32x2")
+#undef MK_F32X2_OP3
+__device__ __forceinline__ void mul2_f32(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void gelu_erf2(float x0, float x1, float& y0, float& y1) {
+  float z0, z1, d0, d1, n0, n1, q0, q1, w0, w1, e0, e1, h0, h1;
+  mul2_f32(z0, z1, fabsf(x0), fabsf(x1), 0.70710678118654752f, 0.70710678118654752f);
+  fma2_f32(d0, d1, z0, z1, 0.3275911f, 0.3275911f, 1.0f, 1.0f);
+  const float t0 = rcp_approx(d0), t1 = rcp_approx(d1);
+  fma2_f32(n0, n1, t0, t1, -1.061405429f, -1.061405429f, 1.453152027f, 1.453152027f);       // -poly
+  fma2_f32(n0, n1, n0, n1, t0, t1, -1.421413741f, -1.421413741f);
+  fma2_f32(n0, n1, n0, n1, t0, t1, 0.284496736f, 0.284496736f);
+  fma2_f32(n0, n1, n0, n1, t0, t1, -0.254829592f, -0.254829592f);
+  mul2_f32(q0, q1, n0, n1, t0, t1);                                                          // (-poly) * t
+  mul2_f32(w0, w1, z0, z1, -1.4426950408889634f, -1.4426950408889634f);
+  mul2_f32(w0, w1, w0, w1, z0, z1);
+  const float x20 = ex2_approx_f(w0), x21 = ex2_approx_f(w1);
+  fma2_f32(e0, e1, q0, q1, x20, x21, 1.0f, 1.0f);                                            // erf(|x| / sqrt 2)
+  mul2_f32(h0, h1, x0, x1, 0.5f, 0.5f);
+  fma2_f32(y0, y1, h0, h1, copysignf(e0, x0), copysignf(e1, x1), h0, h1);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == ACT_GELU) return gelu_erf(x);
   if (act == ACT_RELU) return fmaxf(x, 0.0f);
@@ -359,10 +394,15 @@ __device__ __forceinline__ void epilogue_rows_impl(const GemmParams& p, int g, i
       const int r = (s0 + u) * RPS + rsub;
       const size_t m = (size_t)(row0 + r);
       if constexpr (EPI == EPI_STORE_H) {
+        if constexpr (ACT == ACT_GELU) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float t = v[u][k] + bias[k];
-          v[u][k] = (ACT == ACT_GELU) ? gelu_erf(t) : ((ACT == ACT_RELU) ? fmaxf(t, 0.f) : t);
+          for (int k = 0; k < 8; k += 2) gelu_erf2(v[u][k] + bias[k], v[u][k + 1] + bias[k + 1], v[u][k], v[u][k + 1]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float t = v[u][k] + bias[k];
+            v[u][k] = (ACT == ACT_RELU) ? fmaxf(t, 0.f) : t;
+          }
         }
         st8h(out_h + m * p.out_h_ld, v[u]);
       } else if constexpr (EPI == EPI_RESID_F) {
