@@ -307,7 +307,9 @@ static int launch_2sm_s(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap
 template <int EPI>
 static int launch_2sm(dim3 tiles256, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   const int forced = two_sm_stages_forced();
-  const int st = forced ? forced : (p.k_chunks >= TWO_SM_LONG_K_CHUNKS ? 5 : 4);
+  // the plain fp16 store (attn.qkv) also takes the deeper ring: 338 -> 330 us on 64 images of ViT-B (session 17)
+  const bool plain_h = (EPI == EPI_STORE_H) && p.act == ACT_NONE && p.k_chunks >= 8;
+  const int st = forced ? forced : ((p.k_chunks >= TWO_SM_LONG_K_CHUNKS || plain_h) ? 5 : 4);
   if constexpr (EPI == EPI_STORE_H || EPI == EPI_RESID_F || EPI == EPI_STORE_F) {
     // Short K: a heavy epilogue needs more issue slots than two warps per sub-partition give.  16 epilogue warps (four per
     // TMEM lane quadrant, 32-column passes) measured against 8 on 64 images of ViT-B: mlp.fc1 + GELU 546 -> 516 us alone,
@@ -380,6 +382,8 @@ static int launch_one(const GemmOperand& A, const GemmOperand& B, const GemmPara
       if (three_enabled() && p.k_chunks <= 8 && ctas > 2LL * sm_count() && ctas <= 3LL * sm_count())
         return launch_tc<BN, EPI, 2>(grid, tmA, tmB, p, stream);
     }
+    // (Short-K head GEMMs, K = 128 / 256 with LayerNorm or fp32-store epilogues, were also tried on one-tile CTAs, two per
+    // SM: att.qkv 0.78 -> 1.22 ms, mlp.0 0.34 -> 0.69 ms per C3 step -- the persistent kernel stays; session 20.)
     // Persistent tile loop (accumulator double-buffered in TMEM, ring never drains) when the main loop dominates a
     // tile (K >= 768) or there are many tiles per SM.  Measured on B200: +29 % on the ViT-B GEMMs of the B=32
     // workload (523 -> 674 TFLOP/s), 1.13 PFLOP/s on a 16384x4096x4096 GEMM; but for the K=384, ~2-tiles-per-SM GEMMs
