@@ -69,7 +69,7 @@ struct Workspace {
   // matcher
   float *part_row, *part_col, *lse_r, *lse_c;
   // solver
-  void* samp_ws; int* idx; float* xyw; float* hyp_scores; float* hyp_Rt; int* status; int* best_hyp;
+  void* samp_ws; int* idx; float* hyp_scores; float* hyp_Rt; int* status; int* best_hyp;
   size_t bytes;
 };
 
@@ -104,10 +104,9 @@ Workspace carve(void* base, const mk_config& c, const Geo& g, int n_pairs) {
   const size_t streams = (size_t)n_pairs * c.it_matches;
   w.samp_ws = cv.take<uint8_t>(sampler_workspace_bytes(n_pairs, c.it_matches));
   w.idx = cv.take<int>(streams * c.num_sampled);
-  w.xyw = cv.take<float>(streams * 8 * c.num_sampled);
   w.hyp_scores = cv.take<float>(streams * c.it_ransac);
   w.hyp_Rt = cv.take<float>(streams * c.it_ransac * 12);
-  w.status = cv.take<int>(4);
+  w.status = cv.take<int>(SOLVER_COUNTER_BASE + n_pairs);     // status bits + the fused solver's completion counters
   w.best_hyp = cv.take<int>(n_pairs);
   w.bytes = cv.off + 256;
   return w;
@@ -393,7 +392,7 @@ int run_solve(mk_handle* h, const float* final_scores, long long nn_pitch, const
   RansacParams rp{c.it_matches, c.it_ransac, c.num_sampled, c.num_corr, c.num_refine, c.th_inlier, c.th_soft_inlier, h->seed_dev};
   if (nn_pitch <= 0) nn_pitch = N;
   if (seed != 0) MK_TRY(seed_set(h->seed_dev, seed, st));      // seed == 0: continue the device-side sequence
-  MK_CUDA_CHECK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
+  MK_CUDA_CHECK(cudaMemsetAsync(w.status, 0, (size_t)(SOLVER_COUNTER_BASE + n_pairs) * sizeof(int), st));
   const size_t n_idx = (size_t)n_pairs * c.it_matches * c.num_sampled;
   const int* idx = outer_idx;
   if (!idx) {
@@ -406,8 +405,8 @@ int run_solve(mk_handle* h, const float* final_scores, long long nn_pitch, const
   const float* d0 = depth;
   const float* d1 = depth + (size_t)n_pairs * N;
   int* bs = best_set ? best_set : w.best_hyp;     // scratch when the caller does not want it
-  { ProfScope ps_(h, "solve.ransac", st); h->launches += 3;
-    MK_TRY(ransac_solve(final_scores, nn_pitch, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.xyw, w.hyp_scores,
+  { ProfScope ps_(h, "solve.ransac", st); h->launches += 1;
+    MK_TRY(ransac_solve(final_scores, nn_pitch, kps0, d0, kps1, d1, K0, K1, n_pairs, N, rp, idx, inner_idx, w.hyp_scores,
                         w.hyp_Rt, w.status, pose, bs, inl_mask, best_set ? w.best_hyp : nullptr, st)); }
   MK_TRY(seed_advance(h->seed_dev, st));
   if (sampled_out) MK_CUDA_CHECK(cudaMemcpyAsync(sampled_out, idx, n_idx * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -586,7 +585,7 @@ long long mk_workspace_offset(mk_handle* h, const char* name, int n_pairs, int H
       {"S1", w.S1}, {"O1", w.O1}, {"T2", w.T2}, {"S2", w.S2}, {"O2", w.O2}, {"T3", w.T3}, {"S3", w.S3}, {"CAT", w.CAT},
       {"MSG", w.MSG}, {"HM", w.HM}, {"T4k", w.T4k}, {"S4k", w.S4k}, {"T4d", w.T4d}, {"X32", w.X32}, {"QKV32", w.QKV32},
       {"KV", w.KV}, {"Y4k", w.Y4k}, {"Y4d", w.Y4d}, {"score_raw", w.score_raw}, {"DSCX", w.DSCX}, {"nrm2", w.nrm2},
-      {"lse_r", w.lse_r}, {"lse_c", w.lse_c}, {"idx", w.idx}, {"xyw", w.xyw}, {"hyp_scores", w.hyp_scores},
+      {"lse_r", w.lse_r}, {"lse_c", w.lse_c}, {"idx", w.idx}, {"hyp_scores", w.hyp_scores},
       {"hyp_Rt", w.hyp_Rt}};
   auto it = m.find(name);
   if (it == m.end()) { set_last_error("unknown workspace buffer '%s'", name); return -1; }

@@ -40,7 +40,8 @@ int sample_outer(const float* final_scores, int B, int N, long long pitch, int I
                  void* ws, int* idx_out, int* status, cudaStream_t st);
 int ransac_solve(const float* final_scores, long long pitch, const float* kps0, const float* d0, const float* kps1, const float* d1,
                  const float* K0, const float* K1, int B, int N, const RansacParams& rp, const int* outer_idx,
-                 const int* inner_idx, float* xyw, float* hyp_scores, float* hyp_Rt, int* status, float* pose,
+                 const int* inner_idx, float* hyp_scores, float* hyp_Rt, int* counters, float* pose,
                  int* best_set, float* inl_mask, int* best_hyp, cudaStream_t st);
+constexpr int SOLVER_COUNTER_BASE = 4;      // counters: [0] status bits, [1] pairs finished, [4 + b] blocks of pair b finished
 
 }  // namespace mk

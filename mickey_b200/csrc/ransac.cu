@@ -532,31 +532,43 @@ __device__ __forceinline__ void inv3x3(const float* K, float* Ki) {
   Ki[6] = (float)(C * id);  Ki[7] = (float)(-(a * h - b * g) * id); Ki[8] = (float)((a * e - b * d) * id);
 }
 
-// xyw [B*IM, 8, n_s] (SoA: X0 X1 X2 Y0 Y1 Y2 w pad)
-__global__ void ransac_gather_kernel(const int* __restrict__ idx, const float* __restrict__ fs,
-                                     const float* __restrict__ kps0, const float* __restrict__ d0,
-                                     const float* __restrict__ kps1, const float* __restrict__ d1,
-                                     const float* __restrict__ K0, const float* __restrict__ K1, int N, long long pitch, int IM,
-                                     int n_s, float* __restrict__ xyw) {
-  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
-  pdl_trigger();
-  const int s = blockIdx.x, b = s / IM;
-  __shared__ float Ki0[9], Ki1[9];
-  if (threadIdx.x == 0) { inv3x3(K0 + b * 9, Ki0); inv3x3(K1 + b * 9, Ki1); }
-  __syncthreads();
-  float* o = xyw + (long long)s * 8 * n_s;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n_s; i += gridDim.y * blockDim.x) {   // one sample per thread
-    const int cell = idx[(long long)s * n_s + i];
-    const int i0 = cell / N, i1 = cell - i0 * N;
-    const float u0 = kps0[((long long)b * 2 + 0) * N + i0], v0 = kps0[((long long)b * 2 + 1) * N + i0];
-    const float u1 = kps1[((long long)b * 2 + 0) * N + i1], v1 = kps1[((long long)b * 2 + 1) * N + i1];
-    const float z0 = d0[(long long)b * N + i0], z1 = d1[(long long)b * N + i1];
+// Back-projected 3D points of one set of sampled matches, straight into the block's shared memory (X[3][n_s], Y[3][n_s])
+// together with the per-thread inclusive running sums of the match weights (cdf, when wanted): thread t owns the samples
+// t * per .. t * per + per - 1 (the order the weights' prefix sums are defined in).
+__device__ __forceinline__ void gather_set(const int* __restrict__ idx, const float* __restrict__ fs,
+                                           const float* __restrict__ kps0, const float* __restrict__ d0,
+                                           const float* __restrict__ kps1, const float* __restrict__ d1,
+                                           const float* Ki0, const float* Ki1, int N, long long pitch, int b, long long s, int n_s,
+                                           int n_threads, float* X, float* Y, float* cdf, float& run) {
+  const int per = n_s / n_threads;
+  run = 0.f;
+  // groups of 8 samples: the index -> keypoint / depth / score loads of a group are independent and issued together (the
+  // score is a random access into the N x N matrix: one DRAM round trip per GROUP, not per sample); the running sum follows
+  for (int j0 = 0; j0 < per; j0 += 8) {
+    float wv[8];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      o[r * n_s + i] = z0 * (Ki0[r * 3] * u0 + Ki0[r * 3 + 1] * v0 + Ki0[r * 3 + 2]);
-      o[(3 + r) * n_s + i] = z1 * (Ki1[r * 3] * u1 + Ki1[r * 3 + 1] * v1 + Ki1[r * 3 + 2]);
+    for (int jj = 0; jj < 8; ++jj) {
+      wv[jj] = 0.f;
+      if (j0 + jj < per) {
+        const int i = threadIdx.x * per + j0 + jj;
+        const int cell = idx[s * n_s + i];
+        const int i0 = cell / N, i1 = cell - i0 * N;
+        const float u0 = kps0[((long long)b * 2 + 0) * N + i0], v0 = kps0[((long long)b * 2 + 1) * N + i0];
+        const float u1 = kps1[((long long)b * 2 + 0) * N + i1], v1 = kps1[((long long)b * 2 + 1) * N + i1];
+        const float z0 = d0[(long long)b * N + i0], z1 = d1[(long long)b * N + i1];
+        if (cdf) wv[jj] = fs[(long long)b * N * pitch + (long long)i0 * pitch + i1];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          X[r * n_s + i] = z0 * (Ki0[r * 3] * u0 + Ki0[r * 3 + 1] * v0 + Ki0[r * 3 + 2]);
+          Y[r * n_s + i] = z1 * (Ki1[r * 3] * u1 + Ki1[r * 3 + 1] * v1 + Ki1[r * 3 + 2]);
+        }
+      }
     }
-    o[6 * n_s + i] = fs[(long long)b * N * pitch + (long long)i0 * pitch + i1];
+    if (cdf) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (j0 + jj < per) { run += wv[jj]; cdf[threadIdx.x * per + j0 + jj] = run; }
+    }
   }
 }
 
@@ -662,11 +674,24 @@ __device__ __forceinline__ int cdf_search(const float* cdf, int n, float target)
   return lo;
 }
 
-// grid (groups of hypotheses, IM, B).  smem: X[3][n_s] Y[3][n_s] cdf[n_s]
+// ONE launch per batch: grid (groups of hypotheses, IM, B), 256 threads.  Every block gathers its set of sampled matches
+// into shared memory (X[3][n_s] Y[3][n_s] cdf[n_s]), draws and scores `hyp_per_block` 3-point hypotheses, and counts itself
+// done on its pair; the LAST block of a pair (threadfence + atomic counter) takes the pair's argmax, re-gathers the winning
+// set, runs the refinement and writes the pose; the last pair to finish applies the reference's batch-level zero fallback.
+// `counters`: [0] = status bits, [1] = pairs finished, [4 + b] = blocks of pair b finished (zeroed by the caller).
+constexpr int FIN_THREADS = HYP_THREADS;
+__device__ void finalize_pair(const int* idx, const float* fs, const float* kps0, const float* d0, const float* kps1, const float* d1,
+                              const float* Ki0, const float* Ki1, int N, long long pitch, const float* scores, const float* Rt,
+                              int b, int IM, int IR, int n_s, int n_corr, int n_ref, float th_in, float* sm, float* pose,
+                              int* best_set, float* inl_mask, int* best_hyp);
+
 __global__ void __launch_bounds__(HYP_THREADS)
-ransac_hyp_kernel(const float* __restrict__ xyw, const int* __restrict__ inner_idx, int IM, int IR, int n_s,
-                  int hyp_per_block, float th_soft, const unsigned long long* __restrict__ seed_ptr, float* __restrict__ scores,
-                  float* __restrict__ Rt, int* __restrict__ status) {
+ransac_solve_kernel(const int* __restrict__ idx, const float* __restrict__ fs, const float* __restrict__ kps0,
+                    const float* __restrict__ d0, const float* __restrict__ kps1, const float* __restrict__ d1,
+                    const float* __restrict__ K0, const float* __restrict__ K1, int N, long long pitch,
+                    const int* __restrict__ inner_idx, int IM, int IR, int n_s, int hyp_per_block, float th_soft,
+                    const unsigned long long* __restrict__ seed_ptr, float* scores, float* Rt, int* counters,
+                    int n_corr, int n_ref, float th_in, float* pose, int* best_set, float* inl_mask, int* best_hyp) {
   pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
   pdl_trigger();
   extern __shared__ float sm[];
@@ -674,14 +699,17 @@ ransac_hyp_kernel(const float* __restrict__ xyw, const int* __restrict__ inner_i
   float* Y = sm + 3 * n_s;       // [3][n_s]
   float* cdf = sm + 6 * n_s;     // [n_s] inclusive prefix sums of the weights
   __shared__ float warp_tot[HYP_THREADS / 32];
+  __shared__ float Ki0[9], Ki1[9];
+  __shared__ int last_flag;
+  int* status = counters;
   const int s_in = blockIdx.y, b = blockIdx.z, s = b * IM + s_in;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* src = xyw + (long long)s * 8 * n_s;
-  for (int i = tid; i < 6 * n_s; i += HYP_THREADS) sm[i] = src[i];
+  if (tid == 0) { inv3x3(K0 + b * 9, Ki0); inv3x3(K1 + b * 9, Ki1); }
+  __syncthreads();
   // block-wide inclusive scan of the weights (n_s is a multiple of HYP_THREADS)
   const int per = n_s / HYP_THREADS;
-  float run = 0.f;
-  for (int j = 0; j < per; ++j) { run += src[6 * n_s + tid * per + j]; cdf[tid * per + j] = run; }
+  float run;
+  gather_set(idx, fs, kps0, d0, kps1, d1, Ki0, Ki1, N, pitch, b, s, n_s, HYP_THREADS, X, Y, cdf, run);
   float inc = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -776,10 +804,33 @@ ransac_hyp_kernel(const float* __restrict__ xyw, const int* __restrict__ inner_i
       if (bad) atomicOr(status, 4);
     }
   }
+  // ---- this block is done; the last block of the pair finalizes it ----
+  __syncthreads();
+  const int blocks_per_pair = gridDim.x * gridDim.y;
+  if (tid == 0) {
+    __threadfence();                                   // scores / Rt of this block before the count
+    last_flag = (atomicAdd(&counters[4 + b], 1) == blocks_per_pair - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();                                     // the other blocks' scores / Rt after the count
+  finalize_pair(idx, fs, kps0, d0, kps1, d1, Ki0, Ki1, N, pitch, scores, Rt, b, IM, IR, n_s, n_corr, n_ref, th_in, sm, pose,
+                best_set, inl_mask, best_hyp);
+  // ---- the last pair applies the batch-level zero fallback (probabilisticProcrustes.py:261-262,329-342): too few non-zero
+  // cells (1), a non-finite hypothesis anywhere in the batch (4), and -- never silently -- a truncated candidate list (2)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    last_flag = (atomicAdd(&counters[1], 1) == (int)gridDim.z - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  if ((atomicOr(status, 0) & (1 | 2 | 4)) != 0)
+    for (int i = tid; i < (int)gridDim.z * 13; i += HYP_THREADS) pose[i] = 0.f;
 }
 
 // ---- finalize: argmax + refinement + final score -------------------------------------------------------------------------
-constexpr int FIN_THREADS = 256;
 
 __device__ __forceinline__ void block_reduce_sum(double* vals, int nvals, double* scratch /*[nvals][FIN_THREADS/32]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -798,27 +849,25 @@ __device__ __forceinline__ void block_reduce_sum(double* vals, int nvals, double
   __syncthreads();
 }
 
-// out: pose [B,13] = R (9, row-major) | t (3) | inliers (1);  best_set [B];  inl_mask [B, n_s] (hard inliers @ final pose)
-__global__ void __launch_bounds__(FIN_THREADS)
-ransac_finalize_kernel(const float* __restrict__ xyw, const float* __restrict__ scores, const float* __restrict__ Rt,
-                       int IM, int IR, int n_s, int n_corr, int n_ref, float th_in, const int* __restrict__ status,
-                       float* __restrict__ pose, int* __restrict__ best_set, float* __restrict__ inl_mask,
-                       int* __restrict__ best_hyp) {
-  pdl_wait();        // launched with programmatic stream serialization: predecessors are complete past this point
-  pdl_trigger();
-  extern __shared__ float sm[];
+// out: pose [B,13] = R (9, row-major) | t (3) | inliers (1);  best_set [B];  inl_mask [B, n_s] (hard inliers @ final pose).
+// Runs in the last block of pair b; `scores` / `Rt` were written by other blocks of this launch: L2 loads (__ldcg), never
+// the read-only path.
+__device__ void finalize_pair(const int* idx, const float* fs, const float* kps0, const float* d0, const float* kps1, const float* d1,
+                              const float* Ki0, const float* Ki1, int N, long long pitch, const float* scores, const float* Rt,
+                              int b, int IM, int IR, int n_s, int n_corr, int n_ref, float th_in, float* sm, float* pose,
+                              int* best_set, float* inl_mask, int* best_hyp) {
   float* X = sm;
   float* Y = sm + 3 * n_s;
   __shared__ float red_v[FIN_THREADS];
   __shared__ int red_i[FIN_THREADS];
   __shared__ double scratch[12 * (FIN_THREADS / 32)];
   __shared__ float Rs[9], ts[3];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int total = IM * IR;
   // argmax (first maximal index, like torch.argmax)
   float bv = -INFINITY; int bi = 0x7fffffff;
   for (int i = tid; i < total; i += FIN_THREADS) {
-    const float v = scores[(long long)b * total + i];
+    const float v = __ldcg(scores + (long long)b * total + i);
     if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
   }
   red_v[tid] = bv; red_i[tid] = bi;
@@ -833,10 +882,11 @@ ransac_finalize_kernel(const float* __restrict__ xyw, const float* __restrict__ 
   int best = red_i[0];
   if (best < 0 || best >= total) best = 0;       // all-NaN scores
   const int sset = b * IM + best / IR;
-  const float* src = xyw + (long long)sset * 8 * n_s;
-  for (int i = tid; i < 6 * n_s; i += FIN_THREADS) sm[i] = src[i];
-  if (tid < 9) Rs[tid] = Rt[((long long)b * total + best) * 12 + tid];
-  if (tid < 3) ts[tid] = Rt[((long long)b * total + best) * 12 + 9 + tid];
+  __syncthreads();                               // every thread has read red_i[0] / is done with the hypotheses' X, Y
+  float unused;
+  gather_set(idx, fs, kps0, d0, kps1, d1, Ki0, Ki1, N, pitch, b, sset, n_s, FIN_THREADS, X, Y, nullptr, unused);
+  if (tid < 9) Rs[tid] = __ldcg(Rt + ((long long)b * total + best) * 12 + tid);
+  if (tid < 3) ts[tid] = __ldcg(Rt + ((long long)b * total + best) * 12 + 9 + tid);
   __syncthreads();
 
   auto resid = [&](int i) {
@@ -894,13 +944,10 @@ ransac_finalize_kernel(const float* __restrict__ xyw, const float* __restrict__ 
   }
   block_reduce_sum(acc, 1, scratch);
   if (tid == 0) {
-    // batch-level zero fallback (:261-262,329-342): too few non-zero cells (1), a non-finite hypothesis (4), and -- never
-    // silently -- a truncated candidate list (2; probability < 1e-13 by the threshold's construction)
-    const bool invalid = (*status & (1 | 2 | 4)) != 0;
-    float* o = pose + (long long)b * 13;
-    for (int i = 0; i < 9; ++i) o[i] = invalid ? 0.f : Rs[i];
-    for (int i = 0; i < 3; ++i) o[9 + i] = invalid ? 0.f : ts[i];
-    o[12] = invalid ? 0.f : (float)acc[0];
+    float* o = pose + (long long)b * 13;           // the batch-level zero fallback is applied by the last pair to finish
+    for (int i = 0; i < 9; ++i) o[i] = Rs[i];
+    for (int i = 0; i < 3; ++i) o[9 + i] = ts[i];
+    o[12] = (float)acc[0];
     best_set[b] = sset;
     if (best_hyp) best_hyp[b] = best;
   }
@@ -927,26 +974,23 @@ int seed_advance(unsigned long long* s, cudaStream_t st) {
 
 int ransac_solve(const float* final_scores, long long pitch, const float* kps0, const float* d0, const float* kps1, const float* d1,
                  const float* K0, const float* K1, int B, int N, const RansacParams& rp, const int* outer_idx,
-                 const int* inner_idx, float* xyw, float* hyp_scores, float* hyp_Rt, int* status, float* pose,
+                 const int* inner_idx, float* hyp_scores, float* hyp_Rt, int* counters, float* pose,
                  int* best_set, float* inl_mask, int* best_hyp, cudaStream_t st) {
+  // counters: [0] status bits, [1] pairs finished, [4 + b] blocks of pair b finished; zeroed by the caller before the sampler
   const int IM = rp.it_matches, IR = rp.it_ransac, n_s = rp.n_sample;
   if (rp.n_corr != 3) { set_last_error("NUM_CORR_3D_3D must be 3 (got %d)", rp.n_corr); return MK_ERR_UNSUPPORTED; }
   if (n_s % HYP_THREADS) { set_last_error("NUM_SAMPLED_MATCHES must be a multiple of %d", HYP_THREADS); return MK_ERR_UNSUPPORTED; }
-  MK_CUDA_CHECK(launch_k(ransac_gather_kernel, dim3(B * IM, ceil_div(n_s, 256)), dim3(256), 0, st, outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, pitch, IM, n_s, xyw));
-  MK_CUDA_CHECK(cudaGetLastError());
   const int hyp_per_block = 8;
-  const size_t smem_h = (size_t)7 * n_s * 4, smem_f = (size_t)6 * n_s * 4;
+  const size_t smem_h = (size_t)7 * n_s * 4;
   static unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {
-    MK_CUDA_CHECK(cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    MK_CUDA_CHECK(cudaFuncSetAttribute(ransac_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MK_CUDA_CHECK(cudaFuncSetAttribute(ransac_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   if (smem_h > 200 * 1024) { set_last_error("NUM_SAMPLED_MATCHES too large for shared memory"); return MK_ERR_UNSUPPORTED; }
-  MK_CUDA_CHECK(launch_k(ransac_hyp_kernel, dim3(ceil_div(IR, hyp_per_block), IM, B), dim3(HYP_THREADS), smem_h, st,
-                         xyw, inner_idx, IM, IR, n_s, hyp_per_block, rp.th_soft, rp.seed, hyp_scores, hyp_Rt, status));
-  MK_CUDA_CHECK(cudaGetLastError());
-  MK_CUDA_CHECK(launch_k(ransac_finalize_kernel, dim3(B), dim3(FIN_THREADS), smem_f, st, xyw, hyp_scores, hyp_Rt, IM, IR, n_s, rp.n_corr,
-                         rp.n_refine, rp.th_inlier, status, pose, best_set, inl_mask, best_hyp));
+  MK_CUDA_CHECK(launch_k(ransac_solve_kernel, dim3(ceil_div(IR, hyp_per_block), IM, B), dim3(HYP_THREADS), smem_h, st,
+                         outer_idx, final_scores, kps0, d0, kps1, d1, K0, K1, N, pitch, inner_idx, IM, IR, n_s, hyp_per_block,
+                         rp.th_soft, rp.seed, hyp_scores, hyp_Rt, counters, rp.n_corr, rp.n_refine, rp.th_inlier, pose, best_set,
+                         inl_mask, best_hyp));
   MK_CUDA_CHECK(cudaGetLastError());
   return MK_OK;
 }
