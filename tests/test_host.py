@@ -135,12 +135,21 @@ def test_hot_kernels_are_tcgen05_tma_tmem_in_sass():
     for line in sass.splitlines():
         if "Function :" in line:
             cur = line.split("Function :")[1].strip()
-            per[cur] = {"UTCHMMA": 0, "UTMALDG": 0, "LDTM": 0}
+            per[cur] = {"UTCHMMA": 0, "UTCHMMA.2CTA": 0, "UTMALDG": 0, "UTMASTG": 0, "LDTM": 0, "MEMBAR.ALL.GPU": 0}
         elif cur:
             for k in per[cur]:
                 if k in line:
                     per[cur][k] += 1
-    hot = {n: c for n, c in per.items() if any(t in n for t in ("gemm_tc_kernel", "gemm_tc_persistent_kernel", "attention_tc_kernel"))}
-    assert len(hot) >= 30
+    hot = {n: c for n, c in per.items() if any(t in n for t in ("gemm_tc_kernel", "gemm_tc_persistent_kernel", "gemm_tc_2sm_kernel", "attention_tc_kernel"))}
+    assert len(hot) >= 40
     for name, c in hot.items():
         assert c["UTCHMMA"] > 0 and c["UTMALDG"] > 0 and c["LDTM"] > 0, (name, c)
+    # the cta_group::2 kernels issue the pair-wide MMA, and carry no GPU-scope fence beyond the two of the cluster set-up /
+    # tear-down (a third one used to sit in the accumulator hand-back of every tile)
+    two_sm = {n: c for n, c in hot.items() if "gemm_tc_2sm_kernel" in n}
+    assert len(two_sm) >= 8
+    for name, c in two_sm.items():
+        assert c["UTCHMMA.2CTA"] > 0 and c["MEMBAR.ALL.GPU"] <= 2, (name, c)
+    # matcher pass 2 (EPI_DUAL = 7) leaves through TMA tensor stores
+    dual = {n: c for n, c in hot.items() if "ELi7E" in n and "gemm_tc" in n}
+    assert dual and all(c["UTMASTG"] > 0 for c in dual.values()), dual
