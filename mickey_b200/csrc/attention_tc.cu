@@ -376,15 +376,17 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   if (first_use_on_device(attr_mask)) {
     const void* all[] = {(const void*)attention_tc_kernel<0, 0>, (const void*)attention_tc_kernel<8, 0>, (const void*)attention_tc_kernel<4, 0>,
                          (const void*)attention_tc_kernel<0, 1>, (const void*)attention_tc_kernel<8, 1>, (const void*)attention_tc_kernel<4, 1>,
-                         (const void*)attention_tc_kernel<8, 2>, (const void*)attention_tc_kernel<4, 2>};
+                         (const void*)attention_tc_kernel<8, 2>, (const void*)attention_tc_kernel<4, 2>, (const void*)attention_tc_kernel<3, 2>};
     for (const void* f : all) MK_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     // packed fp32x2 scale / row sum (FFMA2 / FADD2): on by default (64 images, ViT-B: 1113 -> 1081 us with every 4th pair on
     // the FMA-pipe exp2, 1058 us with every 8th).  Every 4th stays the default: the `scores` parity metric, which amplifies
     // the features' error through logits of +-10, was consistently better with it (ViT-L 720x540: 7.9e-4 vs 1.03e-3 for
-    // every 8th and 8.6e-4 for none; profiles/r02_notes.md).  MICKEY_ATTN_PACK2=0 / MICKEY_ATTN_POLY=0|8|4 override.
+    // every 8th and 8.6e-4 for none; profiles/r02_notes.md).  MICKEY_ATTN_PACK2=0|1 / MICKEY_ATTN_POLY=0|8|4|3 override.
     // MICKEY_ATTN_PACK2=2 (default) also evaluates the polynomial on packed pairs: 61 fewer instructions per 64 logits, the
     // same results bit for bit, and the same time (64 images: 1073 vs 1074 us, session 14) -- with every 3rd pair on the
     // polynomial 1052 us, every 2nd 1178 us, every 8th 1117 us: neither the issue slots nor the FMA pipe alone bound the loop.
+    // Every 3rd pair (MICKEY_ATTN_POLY=3, opt-in): 1075 -> 1053 us and C3 630 -> 641 pairs/s on one box (session 22), all parity
+    // tests green, but `scores` of the ViT-L 720x540 fixture moves from 7.9e-4 to 9.9e-4 of the 1e-3 north-star bound: not taken.
     { const char* e = getenv("MICKEY_ATTN_PACK2"); pack = e ? atoi(e) : 2; if (pack < 0 || pack > 2) pack = 2; }
     // default: every 4th pair (25 %) on the FMA pipe -- measured 32.0 -> 29.9 us (one 720x540 pair) and 1156 -> 1100 us
     // (64 images, ViT-B); 12.5 % gives half of that, 50 % is slower than none (issue-bound).  MICKEY_ATTN_POLY=0 disables.
@@ -395,7 +397,7 @@ int attention_tc(const void* qkv, void* out, int n_img, int T, int D, int heads,
   if (rc) return rc;
   dim3 grid(ceil_div(T, FA_BQ), heads, n_img);
   const float scale_log2 = 0.125f * 1.4426950408889634f;
-  auto kern = pack == 2 ? (poly == 8 ? attention_tc_kernel<8, 2> : poly == 4 ? attention_tc_kernel<4, 2> : attention_tc_kernel<0, 1>)
+  auto kern = pack == 2 ? (poly == 8 ? attention_tc_kernel<8, 2> : poly == 4 ? attention_tc_kernel<4, 2> : poly == 3 ? attention_tc_kernel<3, 2> : attention_tc_kernel<0, 1>)
             : pack == 1 ? (poly == 8 ? attention_tc_kernel<8, 1> : poly == 4 ? attention_tc_kernel<4, 1> : attention_tc_kernel<0, 1>)
                         : (poly == 8 ? attention_tc_kernel<8, 0> : poly == 4 ? attention_tc_kernel<4, 0> : attention_tc_kernel<0, 0>);
   MK_CUDA_CHECK(launch_k(kern, grid, dim3(FA_THREADS), (size_t)FA_SMEM, s, tm, (__half*)out, T, D, scale_log2));
