@@ -67,3 +67,13 @@ def test_save_submission_zip_layout(tmp_path):
         lines = z.read("pose_s00001.txt").decode().split("\n")
         assert len(lines) == 2 and lines[1].startswith("seq1/frame_00010.jpg 1.000000 0.000000")
         assert z.read("pose_s00002.txt") == b""
+
+
+def test_uint8_float_round_trip_is_exact():
+    """f1: the uint8 HWC image and the reference's float CHW tensor (lib/datasets/utils.py:74) carry the same information:
+    v / 255 * 255 rounds back to v for every byte, so `from_float_chw(to_float_chw(x)) == x` bit for bit."""
+    from mickey_b200 import io
+    x = torch.arange(256, dtype=torch.uint8).repeat(3 * 4).reshape(4, 256, 3)
+    f = io.to_float_chw(x)
+    assert f.shape == (3, 4, 256) and f.dtype == torch.float32 and float(f.max()) == 1.0
+    assert torch.equal(io.from_float_chw(f), x)
